@@ -1,0 +1,433 @@
+"""In-process multi-device engine: replicate once, then split/run/gather per step.
+
+This is the B200-first re-design of the reference's ``setup_parallel`` +
+``parallel_forward`` closure (/root/reference/any_device_parallel.py:917-1471):
+
+===========================  =====================================================
+reference                    here
+===========================  =====================================================
+closure state + ``_parallel_*``  ``ParallelEngine`` object (same ``_parallel_*`` attrs are
+attrs (ADP:1203-1208, 1452)      still published on the module for tooling parity)
+ThreadPoolExecutor per call      persistent ``DeviceWorker`` threads (parallel/workers.py)
+2x device sync per worker        stream/event ordering only, no host-blocking sync
+blocking ``.to`` + ``torch.cat``   async P2P copies on side streams, peers write their rows
+                                 at final offsets of a pre-allocated output (no cat)
+context re-sent every step       conditioning cache keyed on tensor identity+version (K3)
+CPU-bounce weight clone          D2D clone (utils/replicate.py)
+===========================  =====================================================
+
+When the wrapped module belongs to a model family with a native executor
+(``comfyui_parallelanything_b200.exec``) and the device is a B200, the replica is
+the hand-written sm_100a executor instead of the torch module; the engine logic is
+identical.  The multi-process (one rank per GPU, in-kernel NVLink scatter/gather)
+variant lives in ``parallel/spmd.py``.
+"""
+from __future__ import annotations
+
+import threading
+import time
+import weakref
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import chain as chain_mod
+from .parallel import pipeline as pp
+from .parallel import split as sp
+from .parallel.workers import WorkerPool
+from .utils import dtypes, faults, log, memory, replicate
+from .utils.config import EngineConfig
+
+_PARALLEL_ATTRS = (
+    "_true_parallel_active", "_parallel_devices", "_parallel_streams", "_parallel_weights",
+    "_auto_vram_balance", "_parallel_purge_cache", "_parallel_purge_models", "_parallel_replicas",
+    "_parallel_engine",
+)
+
+
+def _is_oom(e: BaseException) -> bool:
+    return isinstance(e, torch.cuda.OutOfMemoryError) or "out of memory" in str(e).lower()
+
+
+class _Slot:
+    """One active chain entry."""
+    __slots__ = ("index", "name", "device", "replica", "stream", "weight", "worker")
+
+    def __init__(self, index: int, name: str, replica: nn.Module, stream, weight: float):
+        self.index = index
+        self.name = name
+        self.device = torch.device(name)
+        self.replica = replica
+        self.stream = stream
+        self.weight = weight
+        self.worker = None
+
+
+class ParallelEngine:
+    def __init__(self, target_model: nn.Module, device_chain: Sequence, config: Optional[EngineConfig] = None):
+        self.config = (config or EngineConfig()).validate()
+        self.target = target_model
+        self.entries = chain_mod.parse_chain(device_chain)
+        self.slots: List[_Slot] = []
+        self.replicas: Dict[str, nn.Module] = {}
+        self.streams: Dict[str, Any] = {}
+        self.pool = WorkerPool()
+        self.metrics = log.Metrics()
+        self.step = 0
+        self._orig_forward = None
+        self._cond_cache: Dict[Tuple, Any] = {}
+        self._lock = threading.Lock()
+        self.active = False
+
+    # ------------------------------------------------------------------ setup
+    @property
+    def device_names(self) -> List[str]:
+        return [s.name for s in self.slots]
+
+    @property
+    def weights(self) -> List[float]:
+        return [s.weight for s in self.slots]
+
+    @property
+    def lead_device(self) -> torch.device:
+        return self.slots[0].device
+
+    def _merge_duplicate_cuda(self) -> None:
+        seen: Dict[str, int] = {}
+        merged: List[chain_mod.DeviceEntry] = []
+        for e in self.entries:
+            if e.device.startswith("cuda") and e.device in seen:
+                j = seen[e.device]
+                merged[j] = chain_mod.DeviceEntry(e.device, merged[j].percentage + e.percentage)
+                log.warn("device %s listed twice; merged its percentages", e.device)
+                continue
+            seen.setdefault(e.device, len(merged))
+            merged.append(e)
+        self.entries = merged
+
+    def setup(self, has_lora: bool = False, original_device: Optional[torch.device] = None) -> bool:
+        """Replicate onto every chain device.  Returns False (and leaves the model
+        untouched) when nothing usable remains — same contract as ADP:1138-1150."""
+        cfg = self.config
+        self._merge_duplicate_cuda()
+        names = [e.device for e in self.entries]
+        bad = chain_mod.validate_devices(names)
+        if bad is not None:
+            log.error("Invalid device %r in chain; leaving model untouched", bad)
+            return False
+        weights = chain_mod.normalize_weights([e.percentage for e in self.entries])
+        log.info("Using devices: %s", names)
+        log.info("Workload split: %s", [f"{w * 100:.1f}%" for w in weights])
+        safe_attn = {n for n in names if not dtypes.check_sm80_support(n)}
+        for n in sorted(safe_attn):
+            log.info("%s is below SM 8.0: using plain attention on its replica", n)
+
+        if original_device is None:
+            original_device = memory.module_device(self.target) or torch.device("cpu")
+
+        built: List[_Slot] = []
+        try:
+            for i, (name, w) in enumerate(zip(names, weights)):
+                if name in self.replicas:                       # duplicate (cpu,cpu): alias one replica
+                    built.append(_Slot(i, name, self.replicas[name], self.streams.get(name), w))
+                    continue
+                dev = torch.device(name)
+                try:
+                    same = (dev == original_device) or (dev.type == "cpu" and original_device.type == "cpu")
+                    if same and not has_lora:
+                        faults.check_setup(name, i)
+                        replica = self.target
+                        log.info("Reusing original model on %s", name)
+                    else:
+                        if dev.type == "cuda":
+                            log.info("Cloning to %s (free VRAM %.0f MiB)", name, memory.get_free_vram(name))
+                        replica = replicate.safe_model_clone(self.target, dev, safe_attention=name in safe_attn,
+                                                             index=i)
+                        if replica is self.target and has_lora:
+                            # LoRA baked: even the home device gets its own frozen copy (ADP:1073-1086)
+                            replica = replicate._finalize_replica(
+                                replicate.clone_module_d2d(self.target, dev), dev, name in safe_attn)
+                    stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" else None
+                except Exception as e:
+                    if _is_oom(e):
+                        log.warn("OOM while cloning to %s, skipping this device", name)
+                        memory.aggressive_cleanup()
+                        continue
+                    raise
+                self.replicas[name] = replica
+                if stream is not None:
+                    self.streams[name] = stream
+                built.append(_Slot(i, name, replica, stream, w))
+            if not built:
+                raise RuntimeError("no device could hold a replica")
+        except Exception as e:
+            log.error("Parallel setup failed: %s", e)
+            self._drop_replicas()
+            return False
+
+        if len(built) != len(names):                            # renormalise over survivors
+            tot = sum(s.weight for s in built)
+            for s in built:
+                s.weight = s.weight / tot if tot > 0 else 1.0 / len(built)
+            log.info("Surviving devices: %s", [s.name for s in built])
+        for j, s in enumerate(built):
+            s.index = j
+            s.worker = self.pool.add(s.device, s.stream)
+        self.slots = built
+
+        if cfg.workload_split and len(built) > 1:
+            log.info("Configuring pipeline (layer-split) plan for batch=1")
+            pp.wrap_blocks(self.replicas[built[0].name], self.replicas, [s.name for s in built],
+                           [s.weight for s in built])
+        self.active = True
+        return True
+
+    # ------------------------------------------------------------------ forward
+    def _replica_call(self, replica: nn.Module, *a, **k):
+        fn = replica
+        if replica is self.target and self._orig_forward is not None:
+            fn = self._orig_forward
+        return fn(*a, **k)
+
+    def _lead_only(self, x, timesteps, context, kwargs):
+        lead = self.slots[0]
+        with torch.no_grad():
+            return self._replica_call(lead.replica, x, timesteps, context=context, **kwargs)
+
+    def split_sizes(self, batch: int) -> List[int]:
+        names, weights = self.device_names, self.weights
+        if self.config.auto_vram_balance:
+            return chain_mod.split_sizes_vram(batch, names, weights, self.config.split_mode)
+        return chain_mod.split_sizes(batch, weights, self.config.split_mode)
+
+    def forward(self, x, timesteps, context=None, **kwargs):
+        """Replacement for ``diffusion_model.forward(x, timesteps, context=None, **kw)``."""
+        step = self.step
+        self.step += 1
+        try:
+            batch = sp.get_batch_size(x)
+            n = len(self.slots)
+            if batch == 1 and self.config.workload_split:
+                with pp.pipeline_mode(True):
+                    lead = self.slots[0]
+                    return self._replica_call(lead.replica, x, timesteps, context=context, **kwargs)
+            if batch < n or not self.config.workload_split:
+                return self._lead_only(x, timesteps, context, kwargs)
+            sizes = self.split_sizes(batch)
+            active = [(s, z) for s, z in zip(self.slots, sizes) if z > 0]
+            if not active:
+                raise RuntimeError("No active devices available")
+            if len(active) == 1:
+                with torch.no_grad():
+                    return self._replica_call(active[0][0].replica, x, timesteps, context=context, **kwargs)
+            return self._data_parallel(step, batch, active, x, timesteps, context, kwargs)
+        except RuntimeError as e:
+            if _is_oom(e):
+                log.warn("OOM in parallel forward, cleaning up and falling back to the lead device")
+                memory.aggressive_cleanup()
+                self.metrics.incr("oom_fallbacks")
+                return self._lead_only(x, timesteps, context, kwargs)
+            raise
+
+    __call__ = forward
+
+    def _data_parallel(self, step: int, batch: int, active, x, timesteps, context, kwargs):
+        act_sizes = [z for _, z in active]
+        offs = chain_mod.offsets(act_sizes)
+        x_chunks = sp.split_value(x, act_sizes)
+        t_chunks = sp.split_value(timesteps, act_sizes)
+        c_chunks = sp.split_value(context, act_sizes) if context is not None else [None] * len(active)
+        k_chunks = sp.split_kwargs(kwargs, act_sizes, batch)
+        lead_dev = self.lead_device
+        lead_stream = torch.cuda.current_stream(lead_dev) if lead_dev.type == "cuda" else None
+        out_box: Dict[str, Any] = {"buf": None}
+        results: List[Any] = [None] * len(active)
+        t0 = time.perf_counter()
+
+        def run(i: int):
+            slot = active[i][0]
+            dev = slot.device
+            pp.set_pipeline_mode(False)
+            faults.check_step(step, slot.name, slot.index)
+
+            def body():
+                x_in = sp.move_to_device(x_chunks[i], dev, non_blocking=True)
+                t_in = sp.move_to_device(t_chunks[i], dev, non_blocking=True)
+                c_in = self._cached_move(("ctx", i), c_chunks[i], dev)
+                k_in = {k: sp.move_to_device(v, dev, non_blocking=True) for k, v in k_chunks[i].items()}
+                with torch.no_grad():
+                    out = self._replica_call(slot.replica, x_in, t_in, context=c_in, **k_in)
+                # gather: write rows at their final offset on the lead device (no cat)
+                with self._lock:
+                    if out_box["buf"] is None:
+                        out_box["buf"] = sp.output_like(out, batch, lead_dev)
+                buf = out_box["buf"]
+                if buf is None:                     # non-tensor outputs: fall back to concat
+                    return sp.move_to_device(out, lead_dev)
+                sp.write_rows(buf, out, offs[i])
+                return None
+
+            if dev.type == "cuda":
+                with torch.cuda.device(dev):
+                    ctxs = [torch.cuda.stream(slot.stream)] if slot.stream is not None else []
+                    if lead_stream is not None and lead_dev != dev:
+                        ctxs.append(torch.cuda.stream(lead_stream))
+                    with _nested(ctxs):
+                        if slot.stream is not None and lead_stream is not None and lead_dev == dev:
+                            slot.stream.wait_stream(lead_stream)
+                        r = body()
+                        if slot.stream is not None and lead_stream is not None and lead_dev == dev:
+                            lead_stream.wait_stream(slot.stream)
+                        return r
+            return body()
+
+        futures = [active[i][0].worker.submit(lambda i=i: run(i)) for i in range(len(active))]
+        errors: List[Tuple[str, BaseException]] = []
+        for i, f in enumerate(futures):
+            try:
+                results[i] = f.result()
+            except BaseException as e:  # noqa: BLE001 - reported below
+                errors.append((active[i][0].name, e))
+        if errors:
+            for name, e in errors:
+                log.error("on %s: %s", name, e)
+            raise errors[0][1]
+        self.metrics.record(step=step, host_ms=(time.perf_counter() - t0) * 1e3, batch=batch, sizes=act_sizes)
+        if out_box["buf"] is not None:
+            return out_box["buf"]
+        if any(r is None for r in results):
+            missing = [active[i][0].name for i, r in enumerate(results) if r is None]
+            raise RuntimeError(f"Missing results from devices: {missing}")
+        return sp.concatenate_results(results, dim=0)
+
+    def _cached_move(self, key, value, dev):
+        """Conditioning is constant across the steps of one sampling run; re-use the
+        device copy while the source tensor object/version is unchanged."""
+        if value is None or not self.config.cache_conditioning or not isinstance(value, torch.Tensor):
+            return sp.move_to_device(value, dev, non_blocking=True)
+        if value.device == dev:
+            return value
+        sig = (key, str(dev), value.data_ptr(), tuple(value.shape), value.dtype, value._version,
+               tuple(value.stride()))
+        with self._lock:
+            hit = self._cond_cache.get((key, str(dev)))
+        if hit is not None and hit[0] == sig:
+            self.metrics.incr("cond_cache_hits")
+            return hit[1]
+        moved = sp.move_to_device(value, dev, non_blocking=True)
+        with self._lock:
+            self._cond_cache[(key, str(dev))] = (sig, moved, value)   # keep src alive: ptr stays unique
+        return moved
+
+    # ------------------------------------------------------------------ teardown
+    def _drop_replicas(self) -> None:
+        for name, r in list(self.replicas.items()):
+            if r is self.target:
+                continue
+            try:
+                memory.clear_model_caches(r, quiet=True)
+                r.to("meta") if hasattr(r, "to") else None   # free device memory without a D2H copy
+            except Exception:
+                try:
+                    r.cpu()
+                except Exception:
+                    pass
+        self.replicas.clear()
+        self.streams.clear()
+
+    def cleanup(self) -> None:
+        if not self.active and not self.replicas:
+            return
+        log.info("Cleaning up parallel model...")
+        self.active = False
+        for r in self.replicas.values():
+            try:
+                pp.unwrap_blocks(r)
+            except Exception:
+                pass
+        self.pool.shutdown()
+        self._cond_cache.clear()
+        self._drop_replicas()
+        self.slots = []
+        if self.config.purge_models:
+            mm = memory.comfy_mm()
+            if mm is not None:
+                try:
+                    log.info("Purging models from VRAM...")
+                    mm.unload_all_models()
+                except Exception as e:
+                    log.warn("could not unload models: %s", e)
+        if self.config.purge_cache:
+            memory.aggressive_cleanup()
+
+
+class _nested:
+    def __init__(self, ctxs):
+        self.ctxs = ctxs
+
+    def __enter__(self):
+        for c in self.ctxs:
+            c.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        for c in reversed(self.ctxs):
+            c.__exit__(*exc)
+        return False
+
+
+# ---------------------------------------------------------------------- module hook
+
+def cleanup_parallel_model(model_ref) -> None:
+    """Undo ``install`` (ADP:211-282): restore forward, free replicas, drop attrs,
+    unwrap pipeline stages (the reference forgets this), optional purges."""
+    model = model_ref() if isinstance(model_ref, weakref.ref) else model_ref
+    if model is None or not getattr(model, "_true_parallel_active", False):
+        return
+    eng: Optional[ParallelEngine] = getattr(model, "_parallel_engine", None)
+    if "forward" in model.__dict__:
+        try:
+            del model.__dict__["forward"]         # falls back to the class forward
+        except Exception:
+            pass
+    orig = model.__dict__.pop("_original_forward", None)
+    if orig is not None and getattr(orig, "__self__", None) is not model:
+        model.forward = orig                      # an instance-level forward existed before us
+    if eng is not None:
+        eng.cleanup()
+    try:
+        pp.unwrap_blocks(model)
+    except Exception:
+        pass
+    for a in _PARALLEL_ATTRS:
+        if a in model.__dict__:
+            try:
+                delattr(model, a)
+            except Exception:
+                pass
+
+
+def install(engine: ParallelEngine, owner: Any = None) -> None:
+    """Patch ``engine.target.forward`` and publish the reference's ``_parallel_*`` attrs."""
+    import types
+
+    tm = engine.target
+    engine._orig_forward = tm.forward
+
+    def parallel_forward(self, x, timesteps, context=None, **kwargs):
+        return engine.forward(x, timesteps, context=context, **kwargs)
+
+    object.__setattr__(tm, "_original_forward", engine._orig_forward)
+    object.__setattr__(tm, "forward", types.MethodType(parallel_forward, tm))
+    for k, v in (("_true_parallel_active", True), ("_parallel_replicas", engine.replicas),
+                 ("_parallel_devices", engine.device_names), ("_parallel_streams", engine.streams),
+                 ("_parallel_weights", engine.weights), ("_auto_vram_balance", engine.config.auto_vram_balance),
+                 ("_parallel_purge_cache", engine.config.purge_cache),
+                 ("_parallel_purge_models", engine.config.purge_models), ("_parallel_engine", engine)):
+        object.__setattr__(tm, k, v)
+    if owner is not None:
+        try:
+            weakref.finalize(owner, cleanup_parallel_model, weakref.ref(tm))
+        except TypeError:
+            pass

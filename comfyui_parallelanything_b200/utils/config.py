@@ -1,0 +1,55 @@
+"""Config / flag system.
+
+The reference has only ComfyUI widgets (any_device_parallel.py:789-811, 849-865,
+886-910) and no env vars or files.  We keep the widgets (see ``nodes.py``) and add
+a dataclass + environment overrides used by the bench, tests and debugging
+(SURVEY.md §5 "Config / flag system").
+
+Environment variables (all optional):
+
+=====================  ========================================================
+``PA_SPLIT_MODE``      ``compat`` (default; reference arithmetic, repaired when
+                       the reference would produce an invalid split) | ``exact``
+                       (largest-remainder apportionment)
+``PA_BACKEND``         ``auto`` | ``fused`` (sm_100a kernels + in-kernel P2P) |
+                       ``nccl`` (baseline collectives) | ``torch`` (threads)
+``PA_CUDA_GRAPHS``     ``1``/``0`` capture replica forward in CUDA graphs
+``PA_FAULT``           fault injection, e.g. ``oom:cuda:1@setup``,
+                       ``raise:1@step3``, ``oom:1@step2`` (see utils/faults.py)
+``PA_FLAG_TIMEOUT_MS`` watchdog for in-kernel flag waits (default 20000)
+``PA_LOG_LEVEL``       python logging level
+``PA_METRICS_FILE``    JSON-lines metrics sink
+=====================  ========================================================
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+
+def _env_bool(name: str, default: bool) -> bool:
+    v = os.environ.get(name)
+    if v is None:
+        return default
+    return v.strip().lower() not in ("0", "false", "no", "off", "")
+
+
+@dataclass
+class EngineConfig:
+    workload_split: bool = True
+    auto_vram_balance: bool = False       # python default of the reference (ADP:917)
+    purge_cache: bool = True
+    purge_models: bool = False
+    split_mode: str = field(default_factory=lambda: os.environ.get("PA_SPLIT_MODE", "compat"))
+    backend: str = field(default_factory=lambda: os.environ.get("PA_BACKEND", "auto"))
+    cuda_graphs: bool = field(default_factory=lambda: _env_bool("PA_CUDA_GRAPHS", True))
+    flag_timeout_ms: int = field(default_factory=lambda: int(os.environ.get("PA_FLAG_TIMEOUT_MS", "20000")))
+    cache_conditioning: bool = True       # do not re-send constant context every step
+    pair_cfg: bool = False                # keep cond/uncond of one sample on one rank
+
+    def validate(self) -> "EngineConfig":
+        if self.split_mode not in ("compat", "exact"):
+            raise ValueError(f"split_mode must be compat|exact, got {self.split_mode!r}")
+        if self.backend not in ("auto", "fused", "nccl", "torch"):
+            raise ValueError(f"backend must be auto|fused|nccl|torch, got {self.backend!r}")
+        return self

@@ -1,0 +1,212 @@
+"""Engine behaviour + differential tests against the unmodified reference on CPU
+(SURVEY.md §4 items 1-2, Appendix A)."""
+import copy
+import gc
+
+import pytest
+import torch
+import torch.nn as nn
+
+import comfyui_parallelanything_b200 as pa
+from comfyui_parallelanything_b200.models import flux, unet
+from comfyui_parallelanything_b200.parallel import pipeline as pp
+
+
+class Toy(nn.Module):
+    def __init__(self, d=16, n=4):
+        super().__init__()
+        self.hidden_size = d
+        self.inp = nn.Linear(4, d)
+        self.layers = nn.ModuleList([nn.Linear(d, d) for _ in range(n)])
+        self.out = nn.Linear(d, 4)
+        self.calls = []
+
+    def forward(self, x, timesteps, context=None, y=None, **kw):
+        self.calls.append(int(x.shape[0]))
+        h = self.inp(x) + timesteps[:, None]
+        if context is not None:
+            h = h + context.mean(1)
+        if y is not None:
+            h = h + y.sum(-1, keepdim=True)
+        for l in self.layers:
+            h = torch.tanh(l(h))
+        return self.out(h)
+
+
+def chain_of(*pcts, dev="cpu"):
+    c = None
+    for p in pcts:
+        c = pa.ParallelDevice().add_device(dev, p, c)[0]
+    return c
+
+
+def inputs(B, d=16):
+    g = torch.Generator().manual_seed(B)
+    return (torch.randn(B, 4, generator=g), torch.rand(B, generator=g),
+            torch.randn(B, 3, d, generator=g), torch.randn(B, 5, generator=g))
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 6, 21])
+def test_matches_plain_module(B):
+    m, plain = Toy(), Toy()
+    plain.load_state_dict(m.state_dict())
+    out, = pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert out is m and m._true_parallel_active
+    x, t, c, y = inputs(B)
+    with torch.no_grad():
+        got, want = m(x, t, context=c, y=y), plain(x, t, context=c, y=y)
+    assert torch.allclose(got, want, atol=1e-6)
+    pa.cleanup_parallel_model(m)
+
+
+def test_differential_vs_reference(reference):
+    base = Toy()
+    ours, theirs = copy.deepcopy(base), copy.deepcopy(base)
+    pa.ParallelAnything().setup_parallel(ours, chain_of(40, 40, 15, 5), True, False)
+    reference.ParallelAnything().setup_parallel(theirs, chain_of(40, 40, 15, 5), True, False, True, False)
+    for B in (1, 3, 8, 21, 32):
+        x, t, c, y = inputs(B)
+        ours.calls.clear(), theirs.calls.clear()
+        with torch.no_grad():
+            a, b = ours(x, t, context=c, y=y), theirs(x, t, context=c, y=y)
+        assert torch.allclose(a, b, atol=1e-6), B
+        # same split decisions as the reference (cpu entries alias one replica)
+        assert sorted(ours.calls) == sorted(theirs.calls), (B, ours.calls, theirs.calls)
+    pa.cleanup_parallel_model(ours)
+
+
+def test_mode_thresholds():
+    m = Toy()
+    pa.ParallelAnything().setup_parallel(m, chain_of(25, 25, 25, 25))
+    x, t, c, y = inputs(3)
+    m.calls.clear()
+    with torch.no_grad():
+        m(x, t, context=c)
+    assert m.calls == [3]                      # B < n_devices -> lead only
+    x, t, c, y = inputs(4)
+    m.calls.clear()
+    with torch.no_grad():
+        m(x, t, context=c)
+    assert sorted(m.calls) == [1, 1, 1, 1]     # B == n -> DP (code behaviour, ADP:1308)
+    pa.cleanup_parallel_model(m)
+    m2 = Toy()
+    pa.ParallelAnything().setup_parallel(m2, chain_of(50, 50), workload_split=False)
+    m2.calls.clear()
+    with torch.no_grad():
+        m2(*inputs(8)[:2], context=None)
+    assert m2.calls == [8]
+    pa.cleanup_parallel_model(m2)
+
+
+def test_cleanup_restores_everything():
+    m = Toy()
+    fwd_before = m.forward.__func__
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert "forward" in m.__dict__
+    pa.cleanup_parallel_model(m)
+    assert "forward" not in m.__dict__ and m.forward.__func__ is fwd_before
+    assert not any(k.startswith("_parallel") or k == "_true_parallel_active" for k in m.__dict__)
+    assert all(isinstance(l, nn.Linear) for l in m.layers)
+    # second setup never nests wrappers (the reference does)
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert all(not isinstance(getattr(l, "local_block", None), pp.PipelineStage) for l in m.layers)
+    pa.cleanup_parallel_model(m)
+
+
+def test_finalizer_runs_on_owner_gc():
+    class Patcher:
+        def __init__(self, dm):
+            self.model = type("BM", (), {})()
+            self.model.diffusion_model = dm
+            self.load_device = torch.device("cpu")
+            self.patches = {}
+    dm = Toy()
+    p = Patcher(dm)
+    out, = pa.ParallelAnything().setup_parallel(p, chain_of(50, 50))
+    assert out is p and dm._true_parallel_active and p.load_device == torch.device("cpu")
+    del p, out
+    gc.collect()
+    assert not getattr(dm, "_true_parallel_active", False)
+
+
+def test_lora_patches_are_baked_before_clone():
+    class Patcher:
+        def __init__(self, dm):
+            self.model = type("BM", (), {})()
+            self.model.diffusion_model = dm
+            self.load_device = torch.device("cpu")
+            self.patches = {"w": 1}
+            self.baked = False
+        def patch_model(self, device_to=None):
+            with torch.no_grad():
+                self.model.diffusion_model.out.bias.add_(1.0)
+            self.baked = True
+    dm, plain = Toy(), Toy()
+    plain.load_state_dict(dm.state_dict())
+    p = Patcher(dm)
+    pa.ParallelAnything().setup_parallel(p, chain_of(50, 50))
+    assert p.baked
+    x, t, c, y = inputs(4)
+    with torch.no_grad():
+        assert torch.allclose(dm(x, t, context=c), plain(x, t, context=c) + 1.0, atol=1e-6)
+    # with LoRA even the home device runs on a frozen clone
+    assert all(r is not dm for r in dm._parallel_replicas.values())
+    pa.cleanup_parallel_model(dm)
+
+
+def test_fault_injection_oom_paths(monkeypatch):
+    m, plain = Toy(), Toy()
+    plain.load_state_dict(m.state_dict())
+    monkeypatch.setenv("PA_FAULT", "oom:1@step0")
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    x, t, c, y = inputs(6)
+    m.calls.clear()
+    with torch.no_grad():
+        got = m(x, t, context=c)               # worker 1 "OOMs" -> lead-only rerun (ADP:1435-1446)
+    assert torch.allclose(got, plain(x, t, context=c), atol=1e-6)
+    assert 6 in m.calls
+    assert m._parallel_engine.metrics.counters.get("oom_fallbacks") == 1
+    pa.cleanup_parallel_model(m)
+    monkeypatch.setenv("PA_FAULT", "raise:0@step0")
+    m3 = Toy()
+    pa.ParallelAnything().setup_parallel(m3, chain_of(50, 50))
+    with pytest.raises(RuntimeError, match="injected"):
+        m3(x, t, context=c)
+    pa.cleanup_parallel_model(m3)
+
+
+def test_setup_oom_skips_device(monkeypatch):
+    m = Toy()
+    monkeypatch.setenv("PA_FAULT", "oom:cpu@setup")   # every clone target "OOMs" -> rollback
+    out, = pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert out is m and not getattr(m, "_true_parallel_active", False)
+
+
+def test_pipeline_mode_flux_tiny_matches():
+    torch.manual_seed(0)
+    p = flux.flux_tiny_params()
+    m = flux.Flux(p).eval()
+    plain = copy.deepcopy(m)
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert isinstance(m.double_blocks[0], pp.PipelineStage)
+    inp = flux.example_inputs(p, 1, 64, 64, txt_len=8, dtype=torch.float32)
+    with torch.no_grad():
+        assert torch.allclose(m(**inp), plain(**inp), atol=1e-5)
+    inp = flux.example_inputs(p, 4, 64, 64, txt_len=8, dtype=torch.float32)
+    with torch.no_grad():
+        assert torch.allclose(m(**inp), plain(**inp), atol=1e-5)
+    pa.cleanup_parallel_model(m)
+
+
+def test_baseline_config1_sd15_shape_two_cpu_replicas():
+    """BASELINE.json config 1 plumbing (reduced width so it runs in seconds on CPU)."""
+    cfg = unet.tiny_config()
+    m = unet.UNetModel(**cfg).eval()
+    plain = copy.deepcopy(m)
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    inp = unet.example_inputs(cfg, 2, 64, 64, ctx_len=7)
+    x, t, ctx = inp["x"], inp["timesteps"], inp["context"]
+    with torch.no_grad():
+        assert torch.allclose(m(x, t, context=ctx), plain(x, t, context=ctx), atol=1e-5)
+    pa.cleanup_parallel_model(m)

@@ -1,0 +1,91 @@
+"""Replication helpers."""
+import dataclasses
+
+import torch
+import torch.nn as nn
+
+from comfyui_parallelanything_b200.models import flux, unet
+from comfyui_parallelanything_b200.utils import dtypes, memory, replicate
+
+
+def test_fp8_predicates():
+    assert dtypes.is_float8_dtype(torch.float8_e4m3fn) and dtypes.is_float8_dtype(torch.float8_e5m2)
+    assert not dtypes.is_float8_dtype(torch.bfloat16) and not dtypes.is_float8_dtype(None)
+    assert dtypes.check_sm80_support("cpu") and not dtypes.device_supports_float8("cpu")
+    assert dtypes.storage_dtype_for(torch.float8_e4m3fn, "cpu") == torch.float16
+
+
+def test_extract_config_sources():
+    m = flux.Flux(flux.flux_tiny_params())
+    cfg = replicate.extract_model_config(m)
+    assert cfg["hidden_size"] == 256 and cfg["depth"] == 2 and cfg["axes_dim"] == [16, 56, 56]
+    u = unet.UNetModel(**unet.tiny_config())
+    ucfg = replicate.extract_model_config(u)
+    assert ucfg["model_channels"] == 32 and ucfg["channel_mult"] == [1, 2]
+
+
+def test_clone_dataclass():
+    @dataclasses.dataclass
+    class P:
+        a: int
+        t: torch.Tensor
+        l: list
+    p = P(1, torch.ones(2), [torch.zeros(1), 3])
+    q = replicate.clone_dataclass_or_object(p)
+    assert q is not p and q.t is not p.t and torch.equal(q.t, p.t) and q.l[1] == 3
+
+
+def _same(a: nn.Module, b: nn.Module):
+    sa, sb = a.state_dict(), b.state_dict()
+    assert sa.keys() == sb.keys()
+    for k in sa:
+        assert torch.equal(sa[k].float(), sb[k].float()), k
+
+
+def test_three_clone_strategies_agree():
+    m = flux.Flux(flux.flux_tiny_params()).eval()
+    m.img_ids = torch.zeros(3)                      # a device-bound cache that must not follow
+    for fn in (replicate.clone_module_d2d, replicate.clone_module_from_config, replicate.clone_module_structural):
+        c = fn(m, "cpu")
+        assert c is not m
+        _same(m, c)
+        assert next(c.parameters()).data_ptr() != next(m.parameters()).data_ptr()
+    c = replicate._finalize_replica(replicate.clone_module_d2d(m, "cpu"), torch.device("cpu"), False)
+    assert c.img_ids is None and not any(p.requires_grad for p in c.parameters()) and not c.training
+
+
+def test_shared_parameters_stay_shared():
+    class Tied(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(3, 3)
+            self.b = nn.Linear(3, 3)
+            self.b.weight = self.a.weight
+        def forward(self, x):
+            return self.b(self.a(x))
+    c = replicate.clone_module_d2d(Tied(), "cpu")
+    assert c.a.weight is c.b.weight
+
+
+def test_fp8_downcast_on_non_fp8_device():
+    m = nn.Linear(4, 4)
+    m.weight = nn.Parameter(m.weight.detach().to(torch.float8_e4m3fn), requires_grad=False)
+    c = replicate.clone_module_d2d(m, "cpu")
+    assert c.weight.dtype == torch.float16          # cpu has no fp8 support -> widened (ADP:403-404)
+
+
+def test_safe_clone_same_device_returns_source():
+    m = nn.Linear(2, 2)
+    assert replicate.safe_model_clone(m, "cpu") is m
+
+
+def test_clear_caches_and_disable_flash():
+    m = flux.Flux(flux.flux_tiny_params())
+    m.freqs_cis = torch.ones(1)
+    m.double_blocks[0].kv_cache = torch.ones(1)
+    assert memory.clear_model_caches(m, quiet=True) == 2 and m.freqs_cis is None
+    m.double_blocks[0].img_attn.use_flash_attention = True
+    m.use_xformers = True
+    assert memory.disable_flash_xformers(m) >= 2
+    assert m.double_blocks[0].img_attn.use_flash_attention is False and m.use_xformers is False
+    assert memory.get_free_vram("cpu") == 0
