@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoise-steps/sec of FLUX.1-dev (MM-DiT, 11.9 B params, random init),
+1024x1024, global batch 8, bf16 compute, on N GPUs of one node (BASELINE.json config 3).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                      # our engine
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 3     # unmodified reference
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W         # N > 1 (both arms)
+
+One "denoise step" = model forward on the whole batch + the sampler's Euler update
+``x <- x + (sigma' - sigma) * v``.  Strong scaling: the global batch is fixed, ranks split it.
+
+``value``  : device-timed steps/s (CUDA events, barrier + synchronize on both sides, max over ranks),
+             inputs resident on the lead GPU.
+``e2e``    : same metric through the public API with, inside the timed region of every step, the
+             host(pinned)->device copy of that step's inputs and a device->host read of the result.
+Both arms print one JSON line; the reference arm drives the UNMODIFIED reference
+(baseline/_ref/any_device_parallel.py) wrapping the stock-torch FLUX definition from
+``comfyui_parallelanything_b200.models.flux`` (the reference ships no model code of its own).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "denoise-steps/sec (device-timed, max over ranks)"
+MODEL_NAME = "FLUX.1-dev DiT 1024x1024"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self):
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self, n_gpus: int) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                if int(f[0]) >= n_gpus:
+                    continue
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = sorted(s for s, p in zip(sm, power) if p > 300) or sorted(sm)
+        med = busy[len(busy) // 2] if busy else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------- helpers
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def synthetic_inputs(batch: int, pinned: bool):
+    """Synthetic latents / conditioning of the named shape, created on the HOST."""
+    import torch
+    from comfyui_parallelanything_b200.models import flux
+    p = flux.flux_dev_params()
+    inp = flux.example_inputs(p, batch, 1024, 1024, txt_len=512, device="cpu", dtype=torch.bfloat16)
+    sig = torch.tensor([[1.0, 0.96]] * batch, dtype=torch.float32)
+    inp["sig"] = sig
+    if pinned:
+        inp = {k: v.pin_memory() for k, v in inp.items()}
+    return p, inp
+
+
+def max_over_ranks(ms: float, world: int):
+    if world == 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier_sync(world: int):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps: int, warmup: int, world: int):
+    """W untimed warm-up steps, then exactly K steps between CUDA events; returns ms/step (max over ranks)."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    barrier_sync(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    barrier_sync(world)
+    return max_over_ranks(e0.elapsed_time(e1), world) / steps
+
+
+def emit(obj: dict):
+    print(json.dumps(obj), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args) -> int:
+    import torch
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from comfyui_parallelanything_b200 import ops
+    from comfyui_parallelanything_b200.exec.flux_exec import FluxExecutor
+    from comfyui_parallelanything_b200.models import flux
+    ops.require()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    params, host = synthetic_inputs(B, pinned=True)
+    torch.manual_seed(1234)                          # identical random-init weights on every rank
+    with torch.device(dev):
+        model = flux.Flux(params, dtype=torch.bfloat16)
+    ex = FluxExecutor(model, dev)
+    del model
+    torch.cuda.empty_cache()
+
+    result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+    if world == 1:
+        d = {k: v.to(dev) for k, v in host.items()}
+        xs = ex._prep(d["x"], d["timesteps"], d["context"], d["y"], d["guidance"])
+        stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+        out_buf = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16, device=dev)
+
+        def step_device():
+            ex.denoise_step(xs[0], xs[1], xs[2], xs[3], xs[4], d["sig"], out=out_buf)
+
+        def step_e2e():
+            for k in stage:
+                stage[k].copy_(host[k], non_blocking=True)
+            ex.denoise_step(stage["x"], stage["timesteps"], stage["context"], stage["y"], stage["guidance"],
+                            stage["sig"], out=out_buf)
+            result_host.copy_(out_buf, non_blocking=True)
+        comm = 0
+        parallelism = "dp1"
+    else:
+        from comfyui_parallelanything_b200.parallel.spmd import SpmdFluxEngine
+        eng = SpmdFluxEngine(ex, B, 1024, 1024, 512, backend=args.backend)
+        if rank == 0:
+            eng.stage_inputs(host["x"], host["timesteps"], host["context"], host["y"], host["guidance"], host["sig"])
+        torch.cuda.synchronize()
+
+        def step_device():
+            eng.step()
+
+        def step_e2e():
+            if rank == 0:
+                eng.stage_inputs(host["x"], host["timesteps"], host["context"], host["y"], host["guidance"],
+                                 host["sig"])
+            out = eng.step()
+            if rank == 0:
+                result_host.copy_(out, non_blocking=True)
+        parallelism = f"dp{world} ({args.backend}: in-kernel NVLink scatter/gather)" if args.backend == "fused" \
+            else f"dp{world} (nccl baseline)"
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = result_host.numel() * result_host.element_size()
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_device, args.steps, args.warmup, world)
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
+    clocks = sampler.stop(args.gpus) if rank == 0 else {}
+    if world > 1:
+        eng.check_error()
+        launches = (ex.launches_per_step + 8) * args.steps
+    else:
+        launches = ex.launches_per_step * args.steps
+    finite = bool(torch.isfinite(result_host.float()).all().item()) if rank == 0 else True
+    if world > 1:
+        eng.close()
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    if rank == 0:
+        value = 1000.0 / ms
+        emit({"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / 0.0775, 2),
+              "dtype": "bf16", "data": "synthetic latents/conditioning of the named shape, random-init weights",
+              "impl": "ours", "clocks": clocks,
+              "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+              "gpu_launches": launches, "output_finite": finite,
+              "config": {"model": MODEL_NAME, "global_batch": B, "seq_len": 4608, "parallelism": parallelism,
+                         "params_b": 11.9, "l2": "no explicit flush: each step streams 24 GB of weights (>> 126 MB L2)",
+                         "step": "model forward + Euler update (fused into the last GEMM epilogue)"}})
+    return 0
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args) -> int:
+    rank, world, local = dist_env()
+    try:
+        from baseline import ref_loader
+        ref = ref_loader.load()
+    except Exception as e:  # ReferenceUnavailable or import trouble
+        if rank == 0:
+            emit({"impl": "reference", "unavailable": str(e)[:300]})
+        return 0
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ms = ms_e2e = None
+    clocks = {}
+    finite = True
+    B = args.batch
+    h2d = d2h = 0
+    if rank == 0:
+        # The reference is single-process / multi-thread by construction: rank 0 drives all N GPUs
+        # through its own public API; the other torchrun ranks only take part in the barriers.
+        from comfyui_parallelanything_b200.models import flux
+        params, host = synthetic_inputs(B, pinned=True)
+        torch.manual_seed(1234)
+        lead = torch.device("cuda", 0)
+        with torch.device(lead):
+            model = flux.Flux(params, dtype=torch.bfloat16).eval()
+        chain = None
+        pct = 100.0 / args.gpus
+        for i in range(args.gpus):
+            chain = ref.ParallelDevice().add_device(f"cuda:{i}", pct, chain)[0]
+        (model,) = ref.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
+        d = {k: v.to(lead) for k, v in host.items()}
+        stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
+        result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+
+        def euler(x, v, sig):
+            return x + (sig[:, 1] - sig[:, 0]).view(-1, 1, 1, 1).to(x.dtype) * v
+
+        def step_device():
+            with torch.no_grad():
+                v = model(d["x"], d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"])
+                return euler(d["x"], v, d["sig"])
+
+        def step_e2e():
+            for k in stage:
+                stage[k].copy_(host[k], non_blocking=True)
+            with torch.no_grad():
+                v = model(stage["x"], stage["timesteps"], context=stage["context"], y=stage["y"],
+                          guidance=stage["guidance"])
+                result_host.copy_(euler(stage["x"], v, stage["sig"]), non_blocking=True)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = result_host.numel() * result_host.element_size()
+    else:
+        def step_device():
+            return None
+        step_e2e = step_device
+
+    sampler = ClockSampler()
+    if rank == 0:
+        sampler.start()
+    torch.cuda.set_device(0 if rank == 0 else local)
+    ms = timed(step_device, args.steps, args.warmup, world)
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
+    if rank == 0:
+        clocks = sampler.stop(args.gpus)
+        finite = bool(torch.isfinite(result_host.float()).all().item())
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    if rank == 0:
+        value = 1000.0 / ms
+        emit({"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
+              "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
+              "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / 0.0775, 2),
+              "dtype": "bf16", "data": "synthetic latents/conditioning of the named shape, random-init weights",
+              "impl": "reference", "clocks": clocks,
+              "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+              "gpu_launches": 0, "output_finite": finite,
+              "config": {"model": MODEL_NAME, "global_batch": B, "seq_len": 4608,
+                         "parallelism": f"reference threads x{args.gpus} (single process, stock torch kernels)",
+                         "params_b": 11.9, "l2": "no explicit flush: each step streams 24 GB of weights (>> 126 MB L2)",
+                         "step": "model forward (reference hook) + torch Euler update on the lead GPU"}})
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--backend", default=os.environ.get("PA_BACKEND", "fused"), choices=["fused", "nccl"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -135,7 +135,10 @@ class ParallelEngine:
                 dev = torch.device(name)
                 try:
                     same = (dev == original_device) or (dev.type == "cpu" and original_device.type == "cpu")
-                    if same and not has_lora:
+                    native = self._native_replica(dev, name, i)
+                    if native is not None:
+                        replica = native
+                    elif same and not has_lora:
                         faults.check_setup(name, i)
                         replica = self.target
                         log.info("Reusing original model on %s", name)
@@ -182,6 +185,26 @@ class ParallelEngine:
                            [s.weight for s in built])
         self.active = True
         return True
+
+    def _native_replica(self, dev: torch.device, name: str, index: int):
+        """B200 + known model family -> hand-written sm_100a executor packed straight from the
+        source weights (device-to-device), instead of a torch replica."""
+        if self.config.backend == "torch" or dev.type != "cuda":
+            return None
+        from . import exec as native_exec
+        build = native_exec.builder_for(self.target)
+        if build is None:
+            return None
+        from . import ops
+        if not ops.native_ok(dev):
+            if self.config.backend == "fused":
+                raise RuntimeError(f"backend=fused requested but no native library/sm_100 device for {name}: "
+                                   f"{ops.load_error()!r}")
+            return None
+        faults.check_setup(name, index)
+        log.info("Building native sm_100a %s executor on %s (free VRAM %.0f MiB)",
+                 getattr(self.target, "pa_family", "?"), name, memory.get_free_vram(name))
+        return build(self.target, dev, cuda_graphs=self.config.cuda_graphs)
 
     # ------------------------------------------------------------------ forward
     def _replica_call(self, replica: nn.Module, *a, **k):
@@ -326,6 +349,9 @@ class ParallelEngine:
             if r is self.target:
                 continue
             try:
+                if hasattr(r, "release"):
+                    r.release()
+                    continue
                 memory.clear_model_caches(r, quiet=True)
                 r.to("meta") if hasattr(r, "to") else None   # free device memory without a D2H copy
             except Exception:

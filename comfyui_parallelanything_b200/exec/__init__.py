@@ -1,1 +1,22 @@
+"""Native (hand-written sm_100a) executors, one per model family.
 
+``builder_for(module)`` returns ``build(module, device, **kw) -> executor`` when the
+wrapped module is a family we have a static kernel schedule for, else ``None`` (the
+engine then falls back to a torch replica of the module).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch.nn as nn
+
+
+def builder_for(module: nn.Module) -> Optional[Callable]:
+    fam = getattr(module, "pa_family", None)
+    if fam == "flux":
+        from ..models.flux import Flux
+        if isinstance(module, Flux) and module.params.hidden_size // module.params.num_heads == 128 \
+                and module.params.patch_size == 2:
+            from .flux_exec import build_flux_executor
+            return build_flux_executor
+    return None

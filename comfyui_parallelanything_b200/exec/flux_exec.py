@@ -1,0 +1,265 @@
+"""FLUX.1 MM-DiT forward on hand-written sm_100a kernels (the per-replica hot path).
+
+Replaces what the reference reaches through ``forward_fn(x_in, t_in, context=c_in, **k_in)``
+(/root/reference/any_device_parallel.py:1390: thousands of stock torch launches) by a static
+schedule over packed weights:
+
+  * every Linear is the persistent tcgen05/TMEM/TMA GEMM (csrc/kernels/gemm_tcgen05.cuh) with the
+    following work fused into its epilogue: bias, GELU, AdaLN gated residual, the QKV head split +
+    q/k RMSNorm + RoPE (+ the GELU'd MLP half of a single block), and for the last layer
+    unpatchify + Euler update + (NVLink peer) store — the fused "gather";
+  * txt/img streams live in ONE residual buffer ``X[B, Lt+Li, hid]``; the double blocks address
+    the two row ranges as strided 3-D TMA tensors, so no cat/split/chunk kernels exist;
+  * all 96 modulation projections are one GEMM over the concatenated modulation weights;
+  * attention is csrc/kernels/attention.cu (S/O accumulators in TMEM), writing straight into the
+    concat buffer that ``linear2`` of a single block consumes.
+
+Per step: 19*13 + 38*4 + ~12 = ~410 kernel launches, optionally replayed as one CUDA graph.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..models import flux as flux_model
+
+
+def _bf16(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+class FluxExecutor(nn.Module):
+    pa_family = "flux"
+    pa_native = True
+
+    def __init__(self, model: "flux_model.Flux", device, cuda_graphs: bool = False):
+        super().__init__()
+        ops.require()
+        self.device = torch.device(device)
+        p = self.params = model.params
+        self.hid, self.heads = p.hidden_size, p.num_heads
+        if self.hid // self.heads != 128:
+            raise ValueError("FluxExecutor is specialised for head_dim 128")
+        if p.patch_size != 2:
+            raise ValueError("FluxExecutor is specialised for 2x2 patches")
+        self.mlp = int(p.hidden_size * p.mlp_ratio)
+        self.cuda_graphs = cuda_graphs
+        d = self.device
+        W: Dict[str, torch.Tensor] = {}
+
+        def lin(name, m):
+            W[name + ".w"] = _bf16(m.weight, d)
+            W[name + ".b"] = _bf16(m.bias, d) if m.bias is not None else None
+
+        lin("img_in", model.img_in)
+        lin("txt_in", model.txt_in)
+        lin("time_in.in", model.time_in.in_layer)
+        lin("vector_in.in", model.vector_in.in_layer)
+        outs = [model.time_in.out_layer]
+        if p.guidance_embed:
+            lin("guidance_in.in", model.guidance_in.in_layer)
+            outs.append(model.guidance_in.out_layer)
+        outs.append(model.vector_in.out_layer)
+        # vec = sum_i out_i(h_i)  ==  [h_t | h_g | h_y] @ [W_t | W_g | W_y]^T + (b_t + b_g + b_y)
+        W["vec_out.w"] = torch.cat([_bf16(o.weight, d) for o in outs], dim=1).contiguous()
+        W["vec_out.b"] = sum(o.bias.detach().float().to(d) for o in outs).to(torch.bfloat16)
+        mods, self.mod_off = [], {}
+        off = 0
+        for i, blk in enumerate(model.double_blocks):
+            for s in ("img", "txt"):
+                m = getattr(blk, s + "_mod").lin
+                mods.append(m)
+                self.mod_off[("d", i, s)] = off
+                off += m.weight.shape[0]
+                lin(f"d{i}.{s}.qkv", getattr(blk, s + "_attn").qkv)
+                lin(f"d{i}.{s}.proj", getattr(blk, s + "_attn").proj)
+                lin(f"d{i}.{s}.mlp0", getattr(blk, s + "_mlp")[0])
+                lin(f"d{i}.{s}.mlp2", getattr(blk, s + "_mlp")[2])
+                W[f"d{i}.{s}.qs"] = _bf16(getattr(blk, s + "_attn").norm.query_norm.scale, d)
+                W[f"d{i}.{s}.ks"] = _bf16(getattr(blk, s + "_attn").norm.key_norm.scale, d)
+        for i, blk in enumerate(model.single_blocks):
+            mods.append(blk.modulation.lin)
+            self.mod_off[("s", i)] = off
+            off += blk.modulation.lin.weight.shape[0]
+            lin(f"s{i}.l1", blk.linear1)
+            lin(f"s{i}.l2", blk.linear2)
+            W[f"s{i}.qs"] = _bf16(blk.norm.query_norm.scale, d)
+            W[f"s{i}.ks"] = _bf16(blk.norm.key_norm.scale, d)
+        fin = model.final_layer.adaLN_modulation[1]
+        mods.append(fin)
+        self.mod_off[("final",)] = off
+        off += fin.weight.shape[0]
+        self.mod_total = off
+        W["mod.w"] = torch.cat([_bf16(m.weight, d) for m in mods], dim=0).contiguous()
+        W["mod.b"] = torch.cat([_bf16(m.bias, d) for m in mods], dim=0).contiguous()
+        lin("final", model.final_layer.linear)
+        self.W = W
+        self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
+        self._ws: Dict[Tuple, dict] = {}
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self.launches_per_step = 0
+
+    # nn.Module plumbing so engine utilities (module_device, .to("meta") on cleanup) work
+    def parameters(self, recurse: bool = True):  # type: ignore[override]
+        return iter(())
+
+    def release(self) -> None:
+        self.W.clear()
+        self._ws.clear()
+        self._graphs.clear()
+
+    def weight_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.W.values() if t is not None)
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B: int, H: int, Wd: int, Lt: int) -> dict:
+        key = (B, H, Wd, Lt)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        d, hid, mlp = self.device, self.hid, self.mlp
+        Li = (H // 2) * (Wd // 2)
+        L = Lt + Li
+        e = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=d)  # noqa: E731
+        ws = dict(B=B, H=H, Wd=Wd, Lt=Lt, Li=Li, L=L)
+        ws["X"] = e(B, L, hid)
+        ws["XM"] = e(B, L, hid)
+        ws["CAT"] = e(B, L, hid + mlp)
+        ws["Q"], ws["K"], ws["V"] = e(B, self.heads, L, 128), e(B, self.heads, L, 128), e(B, self.heads, L, 128)
+        ws["TOK"] = e(B, Li, self.params.in_channels)
+        ws["T1"], ws["T2"] = e(B, 256), e(B, 256)
+        ws["HC"] = e(B, self.W["vec_out.w"].shape[1])
+        ws["SVEC"] = e(B, hid)
+        ws["MOD"] = e(B, self.mod_total)
+        ws["OUT"] = e(B, self.params.out_channels // 4, H, Wd)
+        m = flux_model.Flux.__new__(flux_model.Flux)
+        m.patch_size = 2
+        ids = flux_model.Flux.make_ids(m, 1, H, Wd, Lt, d)
+        pe = flux_model.EmbedND(128, self.params.theta, self.params.axes_dim)(ids)     # [1,1,L,64,2,2]
+        ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ schedule
+    def _mod(self, ws, key, idx):
+        off = self.mod_off[key] + idx * self.hid
+        return ws["MOD"][:, off:off + self.hid]
+
+    def _run(self, ws, x_ptr: int, t, ctx, y, guidance, out, x_in=None, sigmas=None, out_ptr: Optional[int] = None,
+             out_sample_off: int = 0):
+        W, hid, mlp, Lt, B = self.W, self.hid, self.mlp, ws["Lt"], ws["B"]
+        C = ops.require()
+        n = 0
+        X, XM, CAT, Q, K, V, ROPE = ws["X"], ws["XM"], ws["CAT"], ws["Q"], ws["K"], ws["V"], ws["ROPE"]
+        Xi, Xt = X[:, Lt:], X[:, :Lt]
+        XMi, XMt = XM[:, Lt:], XM[:, :Lt]
+        ATT = CAT[:, :, :hid]
+        MH = CAT[:, :, hid:]
+        # ---- embedders
+        C.patchify(x_ptr, ws["TOK"], B, self.params.in_channels // 4, ws["H"], ws["Wd"], 2)
+        ops.gemm(ws["TOK"], W["img_in.w"], "bias", out=Xi, bias=W["img_in.b"])
+        ops.gemm(ctx, W["txt_in.w"], "bias", out=Xt, bias=W["txt_in.b"])
+        HC = ws["HC"]
+        ops.timestep_embedding(t, 256, out=ws["T1"])
+        ops.gemm(ws["T1"], W["time_in.in.w"], "silu", out=HC[:, :hid], bias=W["time_in.in.b"])
+        col = hid
+        n += 5
+        if self.params.guidance_embed:
+            ops.timestep_embedding(guidance, 256, out=ws["T2"])
+            ops.gemm(ws["T2"], W["guidance_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["guidance_in.in.b"])
+            col += hid
+            n += 2
+        ops.gemm(y, W["vector_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["vector_in.in.b"])
+        ops.gemm(HC, W["vec_out.w"], "silu", out=ws["SVEC"], bias=W["vec_out.b"])          # silu(vec)
+        ops.gemm(ws["SVEC"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])            # all modulations
+        n += 3
+        # ---- double-stream blocks
+        for i in range(self.n_double):
+            for s, xs, xms, seq_off in (("img", Xi, XMi, Lt), ("txt", Xt, XMt, 0)):
+                k = ("d", i, s)
+                ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
+                ops.gemm(xms, W[f"d{i}.{s}.qkv.w"], "qkv_rope", bias=W[f"d{i}.{s}.qkv.b"], q=Q, k=K, v=V,
+                         q_scale=W[f"d{i}.{s}.qs"], k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
+            ops.attention(Q, K, V, out=ATT)
+            n += 5
+            for s, xs, xms, a, mh in (("img", Xi, XMi, ATT[:, Lt:], MH[:, Lt:]), ("txt", Xt, XMt, ATT[:, :Lt], MH[:, :Lt])):
+                k = ("d", i, s)
+                ops.gemm(a, W[f"d{i}.{s}.proj.w"], "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2),
+                         bias=W[f"d{i}.{s}.proj.b"])
+                ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 4), shift=self._mod(ws, k, 3))
+                ops.gemm(xms, W[f"d{i}.{s}.mlp0.w"], "gelu", out=mh, bias=W[f"d{i}.{s}.mlp0.b"])
+                ops.gemm(mh, W[f"d{i}.{s}.mlp2.w"], "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5),
+                         bias=W[f"d{i}.{s}.mlp2.b"])
+                n += 4
+        # ---- single-stream blocks
+        for i in range(self.n_single):
+            k = ("s", i)
+            ops.layernorm_modulate(X, XM, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
+            ops.gemm(XM, W[f"s{i}.l1.w"], "qkv_rope", bias=W[f"s{i}.l1.b"], q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"],
+                     k_scale=W[f"s{i}.ks"], rope=ROPE, seq_off=0, out=CAT, mlp_col_off=hid)
+            ops.attention(Q, K, V, out=ATT)
+            ops.gemm(CAT, W[f"s{i}.l2.w"], "gate_res", out=X, residual=X, gate=self._mod(ws, k, 2), bias=W[f"s{i}.l2.b"])
+            n += 4
+        # ---- final layer: AdaLN + Linear + unpatchify (+ Euler update, + peer store)
+        k = ("final",)
+        ops.layernorm_modulate(Xi, XMi, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
+        kw = dict(bias=W["final.b"], C=self.params.out_channels // 4, Hl=ws["H"], Wl=ws["Wd"],
+                  xout_sample_off=out_sample_off)
+        if out_ptr is not None:
+            kw["x_out_ptr"] = out_ptr
+        else:
+            kw["x_out"] = out
+        if sigmas is not None:
+            kw["sigmas"], kw["x_in"] = sigmas, x_in
+        ops.gemm(XMi, W["final.w"], "euler_unpatch", **kw)
+        n += 2
+        self.launches_per_step = n
+        return out
+
+    # ------------------------------------------------------------------ public entry points
+    def _prep(self, x, timesteps, context, y, guidance):
+        d = self.device
+        B = x.shape[0]
+        bf = lambda t: t.to(device=d, dtype=torch.bfloat16).contiguous()  # noqa: E731
+        x, context = bf(x), bf(context)
+        timesteps = bf(timesteps)
+        if y is None:
+            y = torch.zeros(B, self.params.vec_in_dim, device=d, dtype=torch.bfloat16)
+        y = bf(y[:, :self.params.vec_in_dim])
+        if self.params.guidance_embed:
+            if guidance is None:
+                raise ValueError("guidance-distilled model needs a guidance strength")
+            guidance = bf(guidance)
+        return x, timesteps, context, y, guidance
+
+    @torch.no_grad()
+    def forward(self, x, timesteps, context=None, y=None, guidance=None, control=None, transformer_options=None,
+                **kwargs):
+        """Same contract as ``models.flux.Flux.forward``: returns the velocity [B, 16, H, W]."""
+        with torch.cuda.device(self.device):
+            x, timesteps, context, y, guidance = self._prep(x, timesteps, context, y, guidance)
+            ws = self.workspace(x.shape[0], x.shape[2], x.shape[3], context.shape[1])
+            out = torch.empty_like(x)
+            self._run(ws, x.data_ptr(), timesteps, context, y, guidance, out)
+            return out
+
+    @torch.no_grad()
+    def denoise_step(self, x, timesteps, context, y, guidance, sigmas, out=None, out_ptr=None, out_sample_off=0,
+                     x_src_ptr: Optional[int] = None):
+        """Model forward + Euler update ``x + (sigma_next - sigma) * v`` fused into the last GEMM's
+        epilogue; the result may be stored straight into a peer GPU's buffer (``out_ptr``).
+        ``x_src_ptr`` lets the first kernel pull the latent shard from a peer mapping."""
+        with torch.cuda.device(self.device):
+            ws = self.workspace(x.shape[0], x.shape[2], x.shape[3], context.shape[1])
+            if out is None and out_ptr is None:
+                out = ws["OUT"]
+            self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, y, guidance, out,
+                      x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off)
+            return out
+
+
+def build_flux_executor(model: nn.Module, device, **kw) -> FluxExecutor:
+    return FluxExecutor(model, device, **kw)

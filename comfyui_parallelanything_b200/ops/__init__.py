@@ -1,1 +1,98 @@
+"""Python surface of the native sm_100a library (``_C.so``, built in-tree by
+``tools/build.py`` / ``__graft_entry__.build()``).
 
+On a machine with a CUDA device the extension is mandatory: ``require()`` raises if
+it cannot be loaded — there is deliberately no silent eager fallback for the native
+executors.  On the GPU-less dev box the import is attempted too (it links against
+libtorch only), so build breakage is caught by the CPU test-suite.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+from typing import Optional
+
+import torch
+
+_C = None
+_err: Optional[BaseException] = None
+try:  # noqa: SIM105
+    _C = importlib.import_module(__name__ + "._C")
+except BaseException as e:  # pragma: no cover - depends on build state
+    _err = e
+
+
+def available() -> bool:
+    return _C is not None
+
+
+def load_error() -> Optional[BaseException]:
+    return _err
+
+
+def require():
+    if _C is None:
+        raise RuntimeError(
+            "comfyui_parallelanything_b200 native library is not built/loaded "
+            f"({_err!r}); run `python tools/build.py` (or __graft_entry__.build())")
+    return _C
+
+
+def native_ok(device) -> bool:
+    """True when ``device`` is a Blackwell (sm_100) GPU and the library is loaded."""
+    if _C is None or not torch.cuda.is_available():
+        return False
+    d = torch.device(device)
+    if d.type != "cuda":
+        return False
+    return torch.cuda.get_device_capability(d)[0] == 10
+
+
+EPI = {
+    "bias": 0, "gelu": 1, "silu": 2, "gate_res": 3, "qkv_rope": 4, "euler_unpatch": 5, "geglu": 6, "res": 7,
+}
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, mode: str = "bias", **kw) -> None:
+    """``out = epilogue(a @ w.T)`` on tcgen05 tensor cores.  ``a``: [M,K] or [B,rows,K] view
+    (last dim contiguous), ``w``: [N,K].  See csrc/bind.cpp for the keyword arguments."""
+    require().gemm(a, w, EPI[mode], **kw)
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "bias",
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (w.shape[0],), dtype=torch.bfloat16, device=a.device)
+    gemm(a, w, act, out=out, bias=bias)
+    return out
+
+
+def layernorm_modulate(x, out=None, scale=None, shift=None, gamma=None, beta=None, eps: float = 1e-6):
+    if out is None:
+        out = torch.empty_like(x)
+    require().layernorm_modulate(x, out, scale, shift, gamma, beta, eps)
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int = 256, time_factor: float = 1000.0, max_period: float = 10000.0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(t.shape[0], dim, dtype=torch.bfloat16, device=t.device)
+    require().timestep_embedding(t, out, time_factor, max_period)
+    return out
+
+
+def attention(q, k, v, out=None, scale: Optional[float] = None):
+    """q,k,v: [B,H,L,128] bf16 contiguous -> out [B, Lq, H*128]."""
+    b, h, lq, d = q.shape
+    if out is None:
+        out = torch.empty(b, lq, h * d, dtype=torch.bfloat16, device=q.device)
+    require().attention(q, k, v, out, float(scale if scale is not None else d ** -0.5))
+    return out
+
+
+def groupnorm_silu(x_nhwc, gamma, beta, groups: int = 32, eps: float = 1e-5, silu: bool = True, out=None):
+    if out is None:
+        out = torch.empty_like(x_nhwc)
+    require().groupnorm_silu(x_nhwc, out, gamma, beta, groups, eps, silu)
+    return out

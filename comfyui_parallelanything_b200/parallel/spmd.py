@@ -1,0 +1,244 @@
+"""One-process-per-GPU engine (``torchrun``): replicas on every rank, batch owned by rank 0.
+
+The reference moves shards with ``torch.split`` + N blocking ``.to(dev)`` copies from N Python
+threads and gathers with N blocking ``.to(lead)`` + ``torch.cat``
+(/root/reference/any_device_parallel.py:1348-1356, 1372-1378, 1408, 1433).  Here:
+
+  * every rank allocates one *symmetric* buffer (raw ``cudaMalloc``, exported with CUDA IPC and
+    mapped by all peers — ``SymmetricHeap``); ``torch.distributed`` (NCCL) is used only for
+    bootstrap (handle exchange, barriers) and as the ``backend="nccl"`` baseline;
+  * **scatter**: rank r's first kernel reads its shard of ``x`` / ``t`` / conditioning straight
+    out of rank 0's buffer over NVLink (peer loads inside the patchify / embed kernels) after
+    acquiring a flag word that rank 0 releases once the step's inputs are in place;
+  * **gather**: the last GEMM's epilogue (unpatchify + Euler update) stores rank r's rows of
+    ``x_{t-1}`` directly at their final offset in rank 0's output buffer and releases a
+    per-rank flag; rank 0 acquires all flags — no copy kernels, no cat, no host sync;
+  * flag waits are bounded (watchdog) so a dead peer cannot hang the GPU.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from .. import chain as chain_mod
+from .. import ops
+from ..utils import log
+
+_ALIGN = 1024
+
+
+class SymmetricHeap:
+    """Same-size raw device buffer on every rank, peer-mapped everywhere (CUDA IPC)."""
+
+    def __init__(self, nbytes: int, group=None):
+        C = ops.require()
+        self.C = C
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dev = torch.cuda.current_device()
+        self.nbytes = (nbytes + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.local_ptr = C.dev_malloc(self.dev, self.nbytes, True)
+        handle = C.ipc_get_handle(self.local_ptr)
+        handles: List[Optional[bytes]] = [None] * self.world
+        dist.all_gather_object(handles, (self.dev, handle), group=group)
+        self.ptrs: List[int] = []
+        self._opened: List[int] = []
+        for r, (pdev, h) in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self.local_ptr)
+            else:
+                p = C.ipc_open_handle(self.dev, h)
+                self._opened.append(p)
+                self.ptrs.append(p)
+        self.local = C.tensor_from_ptr(self.local_ptr, self.nbytes, self.dev)
+        self._cursor = 0
+        dist.barrier(group=group)
+
+    def carve(self, nbytes: int) -> int:
+        off = self._cursor
+        self._cursor = (off + nbytes + 255) // 256 * 256
+        if self._cursor > self.nbytes:
+            raise MemoryError("symmetric heap exhausted")
+        return off
+
+    def view(self, off: int, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        return self.local[off:off + nb].view(dtype).view(*shape)
+
+    def peer_ptr(self, rank: int, off: int) -> int:
+        return self.ptrs[rank] + off
+
+    def close(self) -> None:
+        for p in self._opened:
+            try:
+                self.C.ipc_close_handle(p)
+            except Exception:
+                pass
+        self._opened = []
+        if self.local_ptr:
+            self.local = None
+            self.C.dev_free(self.local_ptr)
+            self.local_ptr = 0
+
+
+class SpmdFluxEngine:
+    """SPMD denoise-step engine for the FLUX family.  Every rank calls ``step`` each iteration;
+    only rank 0 passes real inputs (pinned host or device tensors), the others pass ``None``."""
+
+    FLAG_INPUTS = 0          # slot written by rank 0 on every peer: "inputs of epoch e are ready"
+    FLAG_DONE0 = 8           # slots 8.. on rank 0: "rank r finished epoch e"
+
+    def __init__(self, executor, global_batch: int, height: int, width: int, txt_len: int,
+                 weights: Optional[Sequence[float]] = None, split_mode: str = "compat", backend: str = "fused",
+                 timeout_ms: int = 20000):
+        self.ex = executor
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.backend = backend
+        p = executor.params
+        self.B, self.H, self.W, self.Lt = global_batch, height // 8, width // 8, txt_len
+        self.C = p.in_channels // 4
+        w = list(weights) if weights is not None else [1.0 / self.world] * self.world
+        self.sizes = chain_mod.split_sizes(global_batch, chain_mod.normalize_weights(w), split_mode)
+        self.offs = chain_mod.offsets(self.sizes)
+        self.n_local, self.off_local = self.sizes[self.rank], self.offs[self.rank]
+        B = global_batch
+        bf = torch.bfloat16
+        self.spec = {      # name -> (shape, dtype) of rank 0's staging area
+            "x": ((B, self.C, self.H, self.W), bf), "t": ((B,), bf), "ctx": ((B, txt_len, p.context_in_dim), bf),
+            "y": ((B, p.vec_in_dim), bf), "g": ((B,), bf), "sig": ((B, 2), torch.float32),
+            "out": ((B, self.C, self.H, self.W), bf),
+        }
+        total = 4096
+        for shape, dt in self.spec.values():
+            n = 1
+            for s in shape:
+                n *= s
+            total += (n * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        self.heap = SymmetricHeap(total)
+        self.off: Dict[str, int] = {"flags": self.heap.carve(256)}
+        for name, (shape, dt) in self.spec.items():
+            n = 1
+            for s in shape:
+                n *= s
+            self.off[name] = self.heap.carve(n * torch.empty((), dtype=dt).element_size())
+        self.flags = self.heap.view(self.off["flags"], (64,), torch.int32)
+        self.buf = {k: self.heap.view(self.off[k], *self.spec[k]) for k in self.spec}
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.peer_flag_table = torch.tensor([self.heap.peer_ptr(r, self.off["flags"]) for r in range(self.world)],
+                                            dtype=torch.int64, device=self.dev)
+        self.lead_flag_table = torch.tensor([self.heap.peer_ptr(0, self.off["flags"])], dtype=torch.int64,
+                                            device=self.dev)
+        self.timeout_cycles = int(timeout_ms * 1.9e6)
+        self.epoch = 0
+        # local shard buffers (inputs are pulled from rank 0 into these)
+        n = max(self.n_local, 1)
+        e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=self.dev)  # noqa: E731
+        self.loc = dict(x=e(n, self.C, self.H, self.W), t=e(n), ctx=e(n, txt_len, p.context_in_dim),
+                        y=e(n, p.vec_in_dim), g=e(n), sig=e(n, 2, dt=torch.float32))
+        self.comm_launches = 0
+        log.info("SPMD rank %d/%d: samples [%d, %d) of %d, backend=%s", self.rank, self.world, self.off_local,
+                 self.off_local + self.n_local, B, backend)
+
+    # -------------------------------------------------------------- helpers
+    def _src(self, name: str, row_bytes: int) -> int:
+        return self.heap.peer_ptr(0, self.off[name]) + self.off_local * row_bytes
+
+    def _pull(self, name: str) -> None:
+        """Shard of a small tensor: peer -> local with a device-side copy (cudaMemcpyAsync P2P)."""
+        dst = self.loc[name][:self.n_local]
+        row_bytes = dst[0].numel() * dst.element_size() if dst.dim() > 1 else dst.element_size()
+        self.heap.C.memcpy_async(dst.data_ptr(), self._src(name, row_bytes), row_bytes * self.n_local, 4,
+                                 torch.cuda.current_stream().cuda_stream)
+
+    def stage_inputs(self, x, t, ctx, y, g, sig) -> int:
+        """rank 0: copy this step's inputs (pinned host or device tensors) into the symmetric
+        staging area.  Returns the number of bytes copied."""
+        nbytes = 0
+        for name, src in (("x", x), ("t", t), ("ctx", ctx), ("y", y), ("g", g), ("sig", sig)):
+            self.buf[name].copy_(src, non_blocking=True)
+            nbytes += self.buf[name].numel() * self.buf[name].element_size()
+        return nbytes
+
+    # -------------------------------------------------------------- one denoise step
+    def step(self, staged: bool = True) -> torch.Tensor:
+        """All ranks.  Rank 0 must have called ``stage_inputs`` (same stream) before.  Returns rank
+        0's output buffer (valid on rank 0 once the stream reaches this point)."""
+        C = self.heap.C
+        self.epoch += 1
+        e = self.epoch
+        n = 0
+        if self.backend == "nccl":
+            return self._step_nccl()
+        if self.rank == 0:
+            C.signal_flags(self.peer_flag_table, self.world, self.FLAG_INPUTS, e)
+            n += 1
+        C.wait_flags(self.flags, self.FLAG_INPUTS, 1, e, self.timeout_cycles, self.err)
+        n += 1
+        if self.n_local > 0:
+            if self.rank == 0:
+                loc = {k: self.buf[k][self.off_local:self.off_local + self.n_local] for k in ("x", "t", "ctx", "y", "g", "sig")}
+            else:
+                for name in ("x", "t", "ctx", "y", "g", "sig"):
+                    self._pull(name)
+                    n += 1
+                loc = {k: v[:self.n_local] for k, v in self.loc.items()}
+            x_bytes = self.C * self.H * self.W * 2
+            # fused scatter: the patchify/embed kernel loads this rank's latent shard directly from
+            # rank 0's buffer over NVLink; fused gather: the last GEMM epilogue stores x_{t-1} rows at
+            # their final offset in rank 0's output buffer.
+            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"],
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                 x_src_ptr=self._src("x", x_bytes))
+            n += self.ex.launches_per_step
+        C.signal_flags(self.lead_flag_table, 1, self.FLAG_DONE0 + self.rank, e)
+        n += 1
+        if self.rank == 0:
+            C.wait_flags(self.flags, self.FLAG_DONE0, self.world, e, self.timeout_cycles, self.err)
+            n += 1
+        self.comm_launches = n
+        return self.buf["out"]
+
+    def _step_nccl(self) -> torch.Tensor:
+        """Baseline: NCCL point-to-point scatter/gather around the same executor (what "just call
+        the library" costs; not the product path)."""
+        loc = {}
+        for k in ("x", "t", "ctx", "y", "g", "sig"):
+            if self.rank == 0:
+                for r in range(1, self.world):
+                    if self.sizes[r]:
+                        dist.send(self.buf[k][self.offs[r]:self.offs[r] + self.sizes[r]], dst=r)
+                loc[k] = self.buf[k][:self.sizes[0]]
+            else:
+                loc[k] = self.loc[k][:self.n_local]
+                if self.n_local:
+                    dist.recv(loc[k], src=0)
+        out = None
+        if self.n_local:
+            out = self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"])
+        if self.rank == 0:
+            if out is not None:
+                self.buf["out"][:self.sizes[0]].copy_(out)
+            for r in range(1, self.world):
+                if self.sizes[r]:
+                    dist.recv(self.buf["out"][self.offs[r]:self.offs[r] + self.sizes[r]], src=r)
+        elif out is not None:
+            dist.send(out, dst=0)
+        self.comm_launches = self.ex.launches_per_step
+        return self.buf["out"]
+
+    def check_error(self) -> None:
+        v = int(self.err.item()) & 0xFFFFFFFF
+        if v:
+            raise RuntimeError(f"flag wait timed out on rank {self.rank}: 0x{v:08x} (dead or stalled peer)")
+
+    def close(self) -> None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        self.buf, self.flags = {}, None
+        self.heap.close()

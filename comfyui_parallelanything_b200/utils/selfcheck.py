@@ -1,0 +1,344 @@
+"""Numerics self-checks of every native kernel against plain PyTorch fp32 references.
+
+Used three ways: ``pytest -m gpu`` (tests/test_gpu_kernels.py), ``tools/gpu_check.py``
+(each check in its own process so a trapped kernel cannot poison the rest; JSON report
+into ``gpurun_out/``) and ``__graft_entry__.smoke()``.
+Every check returns ``dict(name, max_abs, max_rel, tol, ok, ...)``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+
+CHECKS: Dict[str, Callable[[], dict]] = {}
+
+
+def check(fn):
+    CHECKS[fn.__name__] = fn
+    return fn
+
+
+def _cmp(name: str, got: torch.Tensor, want: torch.Tensor, tol: float, **extra) -> dict:
+    got, want = got.float(), want.float()
+    diff = (got - want).abs()
+    scale = want.abs().mean().item() + 1e-6
+    max_abs = diff.max().item()
+    # error relative to the typical magnitude of the reference (bf16 outputs: ~2^-8 relative)
+    rel = max_abs / scale
+    mean_rel = diff.mean().item() / scale
+    bad = int((diff > tol * scale * 8).sum().item())
+    ok = bool(mean_rel < tol and math.isfinite(max_abs) and bad <= max(1, diff.numel() // 10000))
+    return dict(name=name, max_abs=max_abs, max_rel=rel, mean_rel=mean_rel, tol=tol, ok=ok, outliers=bad,
+                numel=diff.numel(), **extra)
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(device=_dev(), dtype=torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------ GEMM
+def _gemm_ref(a, w, bias=None):
+    y = a.float() @ w.float().t()
+    return y + bias.float() if bias is not None else y
+
+
+@check
+def gemm_bias_small():
+    a, w, b = _rand(300, 256), _rand(512, 256, scale=0.06), _rand(512)
+    out = torch.zeros(300, 512, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(a, w, "bias", out=out, bias=b)
+    return _cmp("gemm_bias_small", out, _gemm_ref(a, w, b), 0.01)
+
+
+@check
+def gemm_bn_variants():
+    a, w, b = _rand(384, 512), _rand(768, 512, scale=0.05), _rand(768)
+    want = _gemm_ref(a, w, b)
+    worst = None
+    for bn in (64, 128, 256):
+        out = torch.zeros(384, 768, dtype=torch.bfloat16, device=_dev())
+        ops.gemm(a, w, "bias", out=out, bias=b, force_bn=bn)
+        r = _cmp(f"gemm_bn{bn}", out, want, 0.01)
+        if worst is None or r["mean_rel"] > worst["mean_rel"]:
+            worst = r
+    worst["name"] = "gemm_bn_variants"
+    return worst
+
+
+@check
+def gemm_flux_shape():
+    """One FLUX linear at full size: M=4608 tokens, K=3072, N=9216 (persistent multi-wave)."""
+    a, w, b = _rand(4608, 3072), _rand(9216, 3072, scale=0.02), _rand(9216)
+    out = torch.empty(4608, 9216, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(a, w, "bias", out=out, bias=b)
+    return _cmp("gemm_flux_shape", out, _gemm_ref(a, w, b), 0.01)
+
+
+@check
+def gemm_batched_strided_views():
+    x = _rand(3, 640, 256)                        # [B, txt(128)+img(512), D]
+    w, b = _rand(256, 256, scale=0.06), _rand(256)
+    out = torch.zeros(3, 640, 256, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(x[:, 128:], w, "bias", out=out[:, 128:], bias=b)
+    ops.gemm(x[:, :128], w, "gelu", out=out[:, :128], bias=b)
+    want = torch.empty(3, 640, 256, device=_dev())
+    want[:, 128:] = _gemm_ref(x[:, 128:], w, b)
+    want[:, :128] = F.gelu(_gemm_ref(x[:, :128], w, b), approximate="tanh")
+    return _cmp("gemm_batched_strided_views", out, want, 0.012)
+
+
+@check
+def gemm_epilogues():
+    a, w, b = _rand(2, 256, 512), _rand(512, 512, scale=0.04), _rand(512)
+    res, gate = _rand(2, 256, 512), _rand(2, 512)
+    y = _gemm_ref(a, w, b)
+    outs, wants = [], []
+    for mode, ref in (("silu", F.silu(y)), ("gelu", F.gelu(y, approximate="tanh")),
+                      ("gate_res", res.float() + gate.float()[:, None] * y), ("res", res.float() + y)):
+        out = torch.zeros(2, 256, 512, dtype=torch.bfloat16, device=_dev())
+        ops.gemm(a, w, mode, out=out, bias=b, residual=res, gate=gate)
+        outs.append(out.float())
+        wants.append(ref)
+    return _cmp("gemm_epilogues", torch.stack(outs), torch.stack(wants), 0.012)
+
+
+@check
+def gemm_skinny_m():
+    a, w, b = _rand(8, 3072), _rand(18432, 3072, scale=0.02), _rand(18432)
+    out = torch.zeros(8, 18432, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(a, w, "bias", out=out, bias=b)
+    return _cmp("gemm_skinny_m", out, _gemm_ref(a, w, b), 0.01)
+
+
+@check
+def gemm_geglu():
+    a = _rand(256, 256)
+    wa, wg, ba, bg = _rand(512, 256, scale=0.06), _rand(512, 256, scale=0.06), _rand(512), _rand(512)
+    want = _gemm_ref(a, wa, ba) * F.gelu(_gemm_ref(a, wg, bg))
+    # interleave rows in groups of 32: [a0..31 | g0..31 | a32..63 | ...]
+    w = torch.stack([wa.view(16, 32, 256), wg.view(16, 32, 256)], 1).reshape(1024, 256).contiguous()
+    b = torch.stack([ba.view(16, 32), bg.view(16, 32)], 1).reshape(1024).contiguous()
+    out = torch.zeros(256, 512, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(a, w, "geglu", out=out, bias=b)
+    return _cmp("gemm_geglu", out, want, 0.012)
+
+
+def _rope_table(L, dev):
+    from ..models import flux
+    ids = torch.zeros(1, L, 3, device=dev)
+    ids[0, :, 1] = torch.arange(L, device=dev) // 16
+    ids[0, :, 2] = torch.arange(L, device=dev) % 16
+    pe = flux.EmbedND(128, 10000, [16, 56, 56])(ids)          # [1,1,L,64,2,2]
+    table = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).contiguous()   # (cos, sin)
+    return pe, table
+
+
+@check
+def gemm_qkv_rope():
+    from ..models import flux
+    B, L, H, D = 2, 384, 2, 128
+    hid = H * D
+    x, w, b = _rand(B, L, hid), _rand(3 * hid + 512, hid, scale=0.06), _rand(3 * hid + 512)
+    qs, ks = (1 + 0.1 * _rand(D).float()).bfloat16(), (1 + 0.1 * _rand(D, seed=3).float()).bfloat16()
+    pe, table = _rope_table(L + 64, _dev())
+    q = torch.zeros(B, H, L + 64, D, dtype=torch.bfloat16, device=_dev())
+    k, v = torch.zeros_like(q), torch.zeros_like(q)
+    cat = torch.zeros(B, L, hid + 512, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(x, w, "qkv_rope", q=q, k=k, v=v, q_scale=qs, k_scale=ks, rope=table, seq_off=64, out=cat,
+             mlp_col_off=hid, bias=b)
+    y = _gemm_ref(x, w, b)
+    qkv, mlp = y[..., :3 * hid], y[..., 3 * hid:]
+    rq, rk, rv = qkv.view(B, L, 3, H, D).permute(2, 0, 3, 1, 4)
+
+    def rms(t, s):
+        return t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * s.float()
+    rq, rk = rms(rq, qs), rms(rk, ks)
+    rq, rk = flux.apply_rope(rq, rk, pe[:, :, 64:])
+    got = torch.cat([q[:, :, 64:].float().flatten(), k[:, :, 64:].float().flatten(), v[:, :, 64:].float().flatten(),
+                     cat[..., hid:].float().flatten()])
+    want = torch.cat([rq.flatten(), rk.flatten(), rv.flatten(), F.gelu(mlp, approximate="tanh").flatten()])
+    r = _cmp("gemm_qkv_rope", got, want, 0.012)
+    r["untouched_prefix_zero"] = bool(q[:, :, :64].abs().max().item() == 0)
+    r["ok"] = r["ok"] and r["untouched_prefix_zero"]
+    return r
+
+
+@check
+def gemm_euler_unpatch():
+    B, C, Hl, Wl, hid = 2, 16, 32, 32, 256
+    L = (Hl // 2) * (Wl // 2)
+    h, w, b = _rand(B, L, hid), _rand(C * 4, hid, scale=0.06), _rand(C * 4)
+    x = _rand(B, C, Hl, Wl)
+    sig = torch.tensor([[1.0, 0.9], [0.5, 0.25]], device=_dev())
+    xo = torch.zeros(B + 1, C, Hl, Wl, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(h, w, "euler_unpatch", bias=b, x_in=x, x_out=xo, xout_sample_off=1, sigmas=sig, C=C, Hl=Hl, Wl=Wl)
+    v = _gemm_ref(h, w, b).view(B, Hl // 2, Wl // 2, C, 2, 2).permute(0, 3, 1, 4, 2, 5).reshape(B, C, Hl, Wl)
+    want = x.float() + (sig[:, 1] - sig[:, 0])[:, None, None, None] * v
+    r = _cmp("gemm_euler_unpatch", xo[1:], want, 0.012)
+    xo2 = torch.zeros(B, C, Hl, Wl, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(h, w, "euler_unpatch", bias=b, x_out=xo2, C=C, Hl=Hl, Wl=Wl)
+    r2 = _cmp("unpatch_only", xo2, v, 0.012)
+    r["ok"] = r["ok"] and r2["ok"] and bool(xo[0].abs().max().item() == 0)
+    r["unpatch_only_mean_rel"] = r2["mean_rel"]
+    return r
+
+
+# ------------------------------------------------------------------------------ attention
+def _attn_case(name, B, H, Lq, Lk, tol=0.02):
+    q, k, v = _rand(B, H, Lq, 128), _rand(B, H, Lk, 128, seed=1), _rand(B, H, Lk, 128, seed=2)
+    out = ops.attention(q, k, v)
+    want = F.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    want = want.transpose(1, 2).reshape(B, Lq, H * 128)
+    return _cmp(name, out, want, tol)
+
+
+@check
+def attention_small():
+    return _attn_case("attention_small", 1, 2, 256, 256)
+
+
+@check
+def attention_ragged():
+    return _attn_case("attention_ragged", 2, 3, 200, 328)     # partial q tile + masked key padding
+
+
+@check
+def attention_flux_len():
+    return _attn_case("attention_flux_len", 1, 4, 4608, 4608)
+
+
+# ------------------------------------------------------------------------------ elementwise
+@check
+def layernorm_modulate():
+    x, sc, sh = _rand(2, 300, 3072), _rand(2, 6, 3072, scale=0.3), _rand(2, 6, 3072, scale=0.3, seed=5)
+    out = ops.layernorm_modulate(x[:, 44:], scale=sc[:, 1], shift=sh[:, 0])
+    want = F.layer_norm(x[:, 44:].float(), (3072,), eps=1e-6) * (1 + sc[:, 1].float()[:, None]) + sh[:, 0].float()[:, None]
+    r = _cmp("layernorm_modulate", out, want, 0.01)
+    g, b = _rand(512), _rand(512, seed=9)
+    x2 = _rand(64, 512)
+    o2 = ops.layernorm_modulate(x2, gamma=g, beta=b, eps=1e-5)
+    r2 = _cmp("ln_affine", o2, F.layer_norm(x2.float(), (512,), g.float(), b.float(), 1e-5), 0.01)
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
+
+
+@check
+def timestep_embedding():
+    from ..models import flux
+    t = torch.tensor([0.0, 0.25, 0.5, 1.0], device=_dev(), dtype=torch.bfloat16)
+    out = ops.timestep_embedding(t, 256)
+    return _cmp("timestep_embedding", out, flux.timestep_embedding(t, 256), 0.01)
+
+
+@check
+def patchify():
+    from ..models import flux
+    m = flux.Flux.__new__(flux.Flux)
+    m.patch_size = 2
+    x = _rand(2, 16, 32, 48)
+    out = torch.zeros(2, 16 * 24, 64, dtype=torch.bfloat16, device=_dev())
+    ops.require().patchify(x.data_ptr(), out, 2, 16, 32, 48, 2)
+    return _cmp("patchify", out, flux.Flux.patchify(m, x), 1e-6)
+
+
+@check
+def groupnorm_silu():
+    x = _rand(2, 320, 24, 24)
+    g, b = _rand(320), _rand(320, seed=4)
+    nhwc = x.permute(0, 2, 3, 1).reshape(2, 576, 320).contiguous()
+    out = ops.groupnorm_silu(nhwc, g, b, 32, 1e-5, True)
+    want = F.silu(F.group_norm(x.float(), 32, g.float(), b.float(), 1e-5)).permute(0, 2, 3, 1).reshape(2, 576, 320)
+    return _cmp("groupnorm_silu", out, want, 0.012)
+
+
+@check
+def cfg_euler_store():
+    x, c, u = _rand(3, 4, 16, 16), _rand(3, 4, 16, 16, seed=1), _rand(3, 4, 16, 16, seed=2)
+    sig = torch.tensor([[1.0, 0.8], [0.8, 0.6], [0.6, 0.1]], device=_dev())
+    out = torch.zeros(5, 4, 16, 16, dtype=torch.bfloat16, device=_dev())
+    ops.require().cfg_euler_store(x, c, u, out.data_ptr(), sig, 7.5, 2, 1)
+    d = u.float() + 7.5 * (c.float() - u.float())
+    want = x.float() + (sig[:, 1] - sig[:, 0])[:, None, None, None] * d
+    r = _cmp("cfg_euler_store", out[2:], want, 0.012)
+    r["ok"] = r["ok"] and bool(out[:2].abs().max().item() == 0)
+    return r
+
+
+@check
+def flags_roundtrip():
+    C = ops.require()
+    flags = torch.zeros(16, dtype=torch.int32, device=_dev())
+    err = torch.zeros(1, dtype=torch.int32, device=_dev())
+    table = torch.tensor([flags.data_ptr()], dtype=torch.int64, device=_dev())
+    C.signal_flags(table, 1, 3, 7)
+    C.wait_flags(flags, 3, 1, 7, 2_000_000_000, err)
+    C.wait_flags(flags, 4, 1, 1, 2_000_000, err)        # never signalled -> watchdog sets err, no hang
+    torch.cuda.synchronize()
+    e = err.item() & 0xFFFFFFFF
+    ok = flags[3].item() == 7 and (e & 0xFFFF0000) == 0xDEAD0000 and (e & 0xFFFF) == 4
+    return dict(name="flags_roundtrip", ok=bool(ok), flag=int(flags[3].item()), err=hex(e))
+
+
+# ------------------------------------------------------------------------------ executors
+def _flux_pair(params, seed=0):
+    from ..exec.flux_exec import FluxExecutor
+    from ..models import flux
+    torch.manual_seed(seed)
+    m = flux.Flux(params).to(device=_dev(), dtype=torch.bfloat16).eval()
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():          # non-trivial norm scales / biases
+            if n_.endswith("scale"):
+                p_.add_(0.1 * torch.randn_like(p_))
+    ex = FluxExecutor(m, _dev())
+    oracle = flux.Flux(params).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    return m, ex, oracle
+
+
+@check
+def flux_executor_tiny():
+    from ..models import flux
+    p = flux.flux_tiny_params()
+    m, ex, oracle = _flux_pair(p)
+    inp = flux.example_inputs(p, 2, 256, 256, txt_len=64, device=_dev(), dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = ex(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+        eager = m(**inp)
+    r = _cmp("flux_executor_tiny", got, want, 0.03)
+    r["eager_bf16_mean_rel"] = _cmp("eager", eager, want, 1.0)["mean_rel"]   # what stock torch bf16 achieves
+    r["launches"] = ex.launches_per_step
+    # fused Euler step == x + dt * v
+    sig = torch.tensor([[1.0, 0.75], [0.5, 0.25]], device=_dev())
+    x, t, c, y, g = ex._prep(inp["x"], inp["timesteps"], inp["context"], inp["y"], inp["guidance"])
+    with torch.no_grad():
+        nxt = ex.denoise_step(x, t, c, y, g, sig).clone()
+    want2 = inp["x"].float() + (sig[:, 1] - sig[:, 0])[:, None, None, None] * want
+    r2 = _cmp("flux_euler", nxt, want2, 0.03)
+    r["euler_mean_rel"] = r2["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
+
+
+@check
+def flux_executor_mid():
+    """Wider/deeper than tiny, ragged token counts (Lt=77, 24x40 latent) to exercise partial tiles."""
+    from ..models import flux
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=512,
+                        mlp_ratio=4.0, num_heads=4, depth=2, depth_single_blocks=3)
+    m, ex, oracle = _flux_pair(p, seed=1)
+    inp = flux.example_inputs(p, 3, 192, 320, txt_len=77, device=_dev(), dtype=torch.bfloat16, seed=3)
+    with torch.no_grad():
+        got = ex(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+    return _cmp("flux_executor_mid", got, want, 0.03)

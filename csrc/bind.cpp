@@ -1,0 +1,238 @@
+// torch <-> native library glue.  Everything below adapts at::Tensor arguments (pointers, strides, the
+// current CUDA stream) to the plain C++ entry points in common/host.h.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include "common/host.h"
+#include "kernels/gemm_params.h"
+#include "runtime/runtime.h"
+
+namespace py = pybind11;
+using at::Tensor;
+
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+static void check(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, "[pa] ", what, " failed with code ", rc, " (", rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "argument error", ")");
+}
+
+static bool has(const py::kwargs& kw, const char* k) { return kw.contains(k) && !kw[k].is_none(); }
+static Tensor ten(const py::kwargs& kw, const char* k) { return kw[k].cast<Tensor>(); }
+static const __nv_bfloat16* bfp(const py::kwargs& kw, const char* k) {
+  if (!has(kw, k)) return nullptr;
+  Tensor t = ten(kw, k);
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16, k, " must be a CUDA bf16 tensor");
+  return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr());
+}
+
+// views: 2-D [M, K] or 3-D [B, rows, K], innermost stride 1
+static void view3(const Tensor& t, int& batch, int& rows, long long& ld, long long& bs) {
+  TORCH_CHECK(t.dim() == 2 || t.dim() == 3, "expected a 2-D or 3-D tensor");
+  TORCH_CHECK(t.stride(-1) == 1, "innermost dimension must be contiguous");
+  if (t.dim() == 2) {
+    batch = 1; rows = (int)t.size(0); ld = t.stride(0); bs = (long long)t.size(0) * t.stride(0);
+  } else {
+    batch = (int)t.size(0); rows = (int)t.size(1); ld = t.stride(1); bs = t.stride(0);
+  }
+}
+
+// gemm(A, W, mode, out=..., bias=..., residual=..., gate=..., q=,k=,v=,q_scale=,k_scale=,rope=,heads=,seq_off=,
+//      mlp_col_off=, qk_eps=, x_in=, x_out= | x_out_ptr=, xout_sample_off=, sigmas=, C=,Hl=,Wl=, force_bn=)
+static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
+  TORCH_CHECK(A.is_cuda() && W.is_cuda(), "gemm: CUDA tensors required");
+  TORCH_CHECK(A.scalar_type() == at::kBFloat16 && W.scalar_type() == at::kBFloat16, "gemm: bf16 required");
+  TORCH_CHECK(W.dim() == 2 && W.stride(1) == 1, "gemm: W must be [N, K] with contiguous K");
+  c10::cuda::CUDAGuard guard(A.device());
+  pa::GemmParams p{};
+  long long lda, abs_;
+  view3(A, p.batch, p.rows, lda, abs_);
+  p.N = (int)W.size(0);
+  p.K = (int)W.size(1);
+  TORCH_CHECK(A.size(-1) == p.K, "gemm: K mismatch");
+  p.mode = mode;
+  if (has(kw, "out")) {
+    Tensor o = ten(kw, "out");
+    int ob, orows;
+    view3(o, ob, orows, p.ldc, p.out_bstride);
+    TORCH_CHECK(ob == p.batch && orows == p.rows, "gemm: out shape mismatch");
+    p.out = reinterpret_cast<__nv_bfloat16*>(o.data_ptr());
+  }
+  p.bias = bfp(kw, "bias");
+  if (has(kw, "residual")) {
+    Tensor r = ten(kw, "residual");
+    int rb, rr;
+    view3(r, rb, rr, p.ldr, p.res_bstride);
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(r.data_ptr());
+  }
+  if (has(kw, "gate")) {
+    Tensor g = ten(kw, "gate");
+    TORCH_CHECK(g.stride(-1) == 1, "gate must be contiguous in its last dim");
+    p.gate = reinterpret_cast<const __nv_bfloat16*>(g.data_ptr());
+    p.gate_bstride = g.dim() >= 2 ? g.stride(0) : 0;
+  }
+  if (mode == pa::EPI_QKV_ROPE) {
+    Tensor q = ten(kw, "q");
+    TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && q.is_contiguous(), "q must be [B, H, L, 128] contiguous");
+    p.q = reinterpret_cast<__nv_bfloat16*>(q.data_ptr());
+    p.k = reinterpret_cast<__nv_bfloat16*>(ten(kw, "k").data_ptr());
+    p.v = reinterpret_cast<__nv_bfloat16*>(ten(kw, "v").data_ptr());
+    p.q_scale = bfp(kw, "q_scale");
+    p.k_scale = bfp(kw, "k_scale");
+    TORCH_CHECK(p.q_scale && p.k_scale, "q_scale/k_scale required");
+    p.heads = (int)q.size(1);
+    p.seq_total = (int)q.size(2);
+    p.seq_off = has(kw, "seq_off") ? kw["seq_off"].cast<int>() : 0;
+    p.qk_eps = has(kw, "qk_eps") ? kw["qk_eps"].cast<float>() : 1e-6f;
+    if (has(kw, "rope")) {
+      Tensor r = ten(kw, "rope");
+      TORCH_CHECK(r.scalar_type() == at::kFloat && r.is_contiguous() && r.size(-1) == 2 && r.size(-2) == 64,
+                  "rope must be float32 [L, 64, 2]");
+      p.rope = reinterpret_cast<const float2*>(r.data_ptr());
+    }
+    p.mlp_cols = p.N - 3 * p.heads * 128;
+    p.mlp_col_off = has(kw, "mlp_col_off") ? kw["mlp_col_off"].cast<long long>() : 0;
+    TORCH_CHECK(p.mlp_cols == 0 || p.out != nullptr, "single-block QKV+MLP needs out=");
+  }
+  if (mode == pa::EPI_EULER_UNPATCH) {
+    p.C = kw["C"].cast<int>();
+    p.Hl = kw["Hl"].cast<int>();
+    p.Wl = kw["Wl"].cast<int>();
+    p.ps = 2;
+    TORCH_CHECK(p.N == p.C * 4, "EULER_UNPATCH expects N == C*4 (2x2 patches)");
+    if (has(kw, "x_in")) p.x_in = bfp(kw, "x_in");
+    if (has(kw, "x_out_ptr")) p.x_out = reinterpret_cast<__nv_bfloat16*>(kw["x_out_ptr"].cast<uintptr_t>());
+    else p.x_out = reinterpret_cast<__nv_bfloat16*>(ten(kw, "x_out").data_ptr());
+    p.xout_sample_off = has(kw, "xout_sample_off") ? kw["xout_sample_off"].cast<long long>() : 0;
+    if (has(kw, "sigmas")) {
+      Tensor s = ten(kw, "sigmas");
+      TORCH_CHECK(s.scalar_type() == at::kFloat && s.is_contiguous(), "sigmas must be float32 [B, 2]");
+      p.sigmas = reinterpret_cast<const float*>(s.data_ptr());
+      TORCH_CHECK(p.x_in != nullptr, "Euler update needs x_in");
+    }
+  } else {
+    TORCH_CHECK(p.out != nullptr || mode == pa::EPI_QKV_ROPE, "gemm: out= required");
+  }
+  int force_bn = has(kw, "force_bn") ? kw["force_bn"].cast<int>() : 0;
+  check(pa::gemm_bf16(A.data_ptr(), lda, abs_, W.data_ptr(), W.stride(0), p, force_bn, cur_stream()), "gemm_bf16");
+}
+
+static void layernorm_modulate(Tensor x, Tensor out, c10::optional<Tensor> scale, c10::optional<Tensor> shift,
+                               c10::optional<Tensor> gamma, c10::optional<Tensor> beta, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  int b, rows, ob, orows;
+  long long ldx, xbs, ldo, obs;
+  view3(x, b, rows, ldx, xbs);
+  view3(out, ob, orows, ldo, obs);
+  TORCH_CHECK(b == ob && rows == orows, "layernorm_modulate: shape mismatch");
+  long long mod_bs = 0;
+  const void *sc = nullptr, *sh = nullptr;
+  if (scale) { sc = scale->data_ptr(); mod_bs = scale->dim() >= 2 ? scale->stride(0) : 0; TORCH_CHECK(scale->stride(-1) == 1); }
+  if (shift) { sh = shift->data_ptr(); long long s2 = shift->dim() >= 2 ? shift->stride(0) : 0; TORCH_CHECK(!scale || s2 == mod_bs, "scale/shift batch strides differ"); mod_bs = s2; }
+  check(pa::layernorm_modulate(x.data_ptr(), ldx, xbs, out.data_ptr(), ldo, obs, sc, sh, mod_bs,
+                               gamma ? gamma->data_ptr() : nullptr, beta ? beta->data_ptr() : nullptr, b, rows,
+                               (int)x.size(-1), (float)eps, cur_stream()),
+        "layernorm_modulate");
+}
+
+static void timestep_embedding(Tensor t, Tensor out, double time_factor, double max_period) {
+  c10::cuda::CUDAGuard guard(t.device());
+  TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kFloat);
+  check(pa::timestep_embedding(t.data_ptr(), out.data_ptr(), out.stride(0), (int)out.size(0), (int)out.size(1),
+                               (float)time_factor, (float)max_period, t.scalar_type() == at::kBFloat16, cur_stream()),
+        "timestep_embedding");
+}
+
+static void patchify(uintptr_t x_ptr, Tensor out, int B, int C, int H, int W, int ps) {
+  c10::cuda::CUDAGuard guard(out.device());
+  int ob, orows;
+  long long ldo, obs;
+  view3(out, ob, orows, ldo, obs);
+  check(pa::patchify(reinterpret_cast<const void*>(x_ptr), out.data_ptr(), ldo, obs, B, C, H, W, ps, cur_stream()),
+        "patchify");
+}
+
+static void silu_(Tensor x, Tensor out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_contiguous() && out.is_contiguous());
+  check(pa::silu_bf16(x.data_ptr(), out.data_ptr(), x.numel(), cur_stream()), "silu");
+}
+
+static void add_(Tensor a, Tensor b, Tensor out) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
+  check(pa::add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), cur_stream()), "add");
+}
+
+static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous());
+  TORCH_CHECK(out.dim() == 3 && out.stride(2) == 1, "out must be [B, L, H*128] (row stride free)");
+  check(pa::attention_d128(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
+                           (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), (float)scale, cur_stream()),
+        "attention_d128");
+}
+
+static void groupnorm_silu(Tensor x, Tensor out, Tensor gamma, Tensor beta, int groups, double eps, bool silu) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 3 && x.is_contiguous() && out.is_contiguous(), "x must be NHWC flattened: [B, HW, C]");
+  Tensor ws = at::zeros({x.size(0) * groups * 2}, x.options().dtype(at::kFloat));
+  check(pa::groupnorm_silu_nhwc_ws(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                   ws.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2), groups,
+                                   (float)eps, silu ? 1 : 0, cur_stream()),
+        "groupnorm_silu");
+}
+
+static void cfg_euler_store(Tensor x, Tensor eps_c, c10::optional<Tensor> eps_u, uintptr_t x_out_ptr,
+                            c10::optional<Tensor> sigmas, double cfg, long long out_sample_off, int mode) {
+  c10::cuda::CUDAGuard guard(eps_c.device());
+  TORCH_CHECK(eps_c.is_contiguous());
+  const int batch = (int)eps_c.size(0);
+  const long long per = eps_c.numel() / batch;
+  check(pa::cfg_euler_store(x.data_ptr(), eps_c.data_ptr(), eps_u ? eps_u->data_ptr() : nullptr,
+                            reinterpret_cast<void*>(x_out_ptr), sigmas ? sigmas->data_ptr() : nullptr, (float)cfg, per,
+                            batch, out_sample_off, mode, cur_stream()),
+        "cfg_euler_store");
+}
+
+static void signal_flags(Tensor peer_ptr_table, int n_peers, int slot, uint32_t value) {
+  c10::cuda::CUDAGuard guard(peer_ptr_table.device());
+  check(pa::signal_flags(reinterpret_cast<uint32_t* const*>(peer_ptr_table.data_ptr()), n_peers, slot, value,
+                         cur_stream()),
+        "signal_flags");
+}
+
+static void wait_flags(Tensor flags, int first, int n, uint32_t value, long long timeout_cycles, Tensor err) {
+  c10::cuda::CUDAGuard guard(flags.device());
+  check(pa::wait_flags(reinterpret_cast<const uint32_t*>(flags.data_ptr()), first, n, value, timeout_cycles,
+                       reinterpret_cast<uint32_t*>(err.data_ptr()), cur_stream()),
+        "wait_flags");
+}
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "comfyui-parallelanything_b200 native library (sm_100a kernels + runtime)";
+  m.def("gemm", &gemm, py::arg("A"), py::arg("W"), py::arg("mode"));
+  m.def("layernorm_modulate", &layernorm_modulate, py::arg("x"), py::arg("out"), py::arg("scale") = py::none(),
+        py::arg("shift") = py::none(), py::arg("gamma") = py::none(), py::arg("beta") = py::none(),
+        py::arg("eps") = 1e-6);
+  m.def("timestep_embedding", &timestep_embedding);
+  m.def("patchify", &patchify);
+  m.def("silu", &silu_);
+  m.def("add", &add_);
+  m.def("attention", &attention);
+  m.def("groupnorm_silu", &groupnorm_silu);
+  m.def("cfg_euler_store", &cfg_euler_store);
+  m.def("signal_flags", &signal_flags);
+  m.def("wait_flags", &wait_flags);
+  m.def("num_sms", &pa::num_sms);
+  pa::rt::bind(m);
+  m.attr("EPI_BIAS") = (int)pa::EPI_BIAS;
+  m.attr("EPI_BIAS_GELU") = (int)pa::EPI_BIAS_GELU;
+  m.attr("EPI_BIAS_SILU") = (int)pa::EPI_BIAS_SILU;
+  m.attr("EPI_GATE_RES") = (int)pa::EPI_GATE_RES;
+  m.attr("EPI_QKV_ROPE") = (int)pa::EPI_QKV_ROPE;
+  m.attr("EPI_EULER_UNPATCH") = (int)pa::EPI_EULER_UNPATCH;
+  m.attr("EPI_GEGLU") = (int)pa::EPI_GEGLU;
+  m.attr("EPI_RES") = (int)pa::EPI_RES;
+}

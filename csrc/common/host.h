@@ -1,0 +1,54 @@
+// Host-callable entry points of the native library (plain C++ signatures, no torch headers, so the
+// .cu files compile in seconds; csrc/bind.cpp adapts them to torch tensors).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pa {
+
+struct GemmParams;
+
+int num_sms();
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int elem_bytes);
+
+int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, GemmParams p,
+              int force_bn, cudaStream_t st);
+
+// out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
+int layernorm_modulate(const void* x, long long ldx, long long x_bstride, void* out, long long ldo,
+                       long long o_bstride, const void* scale, const void* shift, long long mod_bstride,
+                       const void* gamma, const void* beta, int batch, int rows, int D, float eps, cudaStream_t st);
+
+// sinusoidal embedding: out[b, :] = [cos(t*f_i) | sin(t*f_i)], f_i = exp(-ln(max_period) * i / half)
+int timestep_embedding(const void* t, void* out, long long ldo, int B, int dim, float time_factor,
+                       float max_period, int t_is_bf16, cudaStream_t st);
+
+// x[b, c, H, W] (NCHW latent, possibly on a peer GPU) -> tokens[b, (h w), (c ph pw)]
+int patchify(const void* x, void* out, long long ldo, long long o_bstride, int B, int C, int H, int W, int ps,
+             cudaStream_t st);
+
+// elementwise helpers
+int silu_bf16(const void* x, void* out, long long n, cudaStream_t st);
+int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st);
+
+// fused attention (head_dim 128, bf16): q,k,v [BH, L, 128] -> out[b, l, h*128 + d] with row stride ldo
+int attention_d128(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride,
+                   int B, int H, int Lq, int Lk, float scale, cudaStream_t st);
+
+// GroupNorm (+ optional SiLU) on NHWC bf16
+int groupnorm_silu_nhwc_ws(const void* x, void* out, const void* gamma, const void* beta, float* workspace, int B,
+                           int HW, int C, int groups, float eps, int apply_silu, cudaStream_t st);
+
+// CFG + Euler update + peer store (elementwise "gather" for models whose last op is not a GEMM)
+int cfg_euler_store(const void* x, const void* eps_cond, const void* eps_uncond, void* x_out, const void* sigmas,
+                    float cfg_scale, long long n_per_sample, int batch, long long out_sample_off, int mode,
+                    cudaStream_t st);
+
+// flag words (release/acquire at .sys scope) for the cross-GPU step protocol
+int signal_flags(uint32_t* const* peer_flag_ptrs, int n_peers, int slot, uint32_t value, cudaStream_t st);
+int wait_flags(const uint32_t* flags, int first_slot, int n_slots, uint32_t value, long long timeout_cycles,
+               uint32_t* error_word, cudaStream_t st);
+
+}  // namespace pa

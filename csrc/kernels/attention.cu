@@ -1,0 +1,304 @@
+// Fused attention for head_dim 128 (DiT joint attention; RoPE / q-k RMSNorm are already applied by the
+// QKV GEMM epilogue), bf16 in/out, fp32 softmax, non-causal.
+//
+// One CTA = one 128-row Q tile of one (batch, head).  Warp roles:
+//   warp 0   TMA producer: Q once, then K_j / V_j tiles (128 keys) through 2-stage rings
+//   warp 1   tcgen05.mma issuer:  S_j = Q K_j^T  (TMEM, double buffered)  and  O_j = P_j V_j (TMEM, double buffered)
+//   warp 2   TMEM allocator
+//   warps 4-7  softmax: thread == query row.  Two passes over S_j in TMEM (row max, then exp2 + row sum),
+//            P_j written to shared memory as a 128B-swizzled K-major A operand, running output kept in
+//            registers: O = O * alpha_j + O_j.
+// V is consumed as an MN-major B operand straight from its natural [keys, d] layout (no transpose).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+
+namespace pa {
+
+namespace attn {
+constexpr int BM = 128, BN = 128, D = 128;
+constexpr uint32_t TILE_BYTES = 128 * 128 * 2;     // 32 KB: two 16 KB slices of [128 rows][64 elems]
+constexpr uint32_t SLICE_BYTES = 128 * 64 * 2;
+constexpr uint32_t OFF_Q = 0;
+constexpr uint32_t OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
+constexpr uint32_t OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
+constexpr uint32_t OFF_P = OFF_V + 2 * TILE_BYTES;
+constexpr uint32_t OFF_BAR = OFF_P + TILE_BYTES;
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr uint32_t TMEM_COLS = 512;                 // S0 S1 O0 O1, 128 fp32 columns each
+}  // namespace attn
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256, 1)
+attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
+                      long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
+  using namespace attn;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_empty = bars + 11;      // 2
+  uint64_t* o_full = bars + 13;       // 2
+  uint64_t* o_empty = bars + 15;      // 2
+  uint64_t* p_full = bars + 17;       // 1
+  uint64_t* p_empty = bars + 18;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM;
+  const int bh = blockIdx.y;
+  const int n_kv = (Lk + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&s_empty[i], 4);
+      ptx::mbar_init(&o_full[i], 1);
+      ptx::mbar_init(&o_empty[i], 4);
+    }
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(p_empty, 1);
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      ptx::tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
+      ptx::tma_load_3d(smem + OFF_Q + SLICE_BYTES, &tmQ, q_full, 64, q0, bh);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        ptx::tma_load_3d(smem + OFF_K + s * TILE_BYTES, &tmK, &k_full[s], 0, j * BN, bh);
+        ptx::tma_load_3d(smem + OFF_K + s * TILE_BYTES + SLICE_BYTES, &tmK, &k_full[s], 64, j * BN, bh);
+        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        ptx::tma_load_3d(smem + OFF_V + s * TILE_BYTES, &tmV, &v_full[s], 0, j * BN, bh);
+        ptx::tma_load_3d(smem + OFF_V + s * TILE_BYTES + SLICE_BYTES, &tmV, &v_full[s], 64, j * BN, bh);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
+      constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, 128, 1, 0, 1);   // B (= V) is MN-major
+      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
+      const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
+      auto issue_qk = [&](int i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        ptx::mbar_wait(&k_full[s], ph);
+        ptx::mbar_wait(&s_empty[s], ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t k_addr = ptx::smem_u32(smem + OFF_K + s * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * SLICE_BYTES + (kk & 3) * 32;
+          ptx::mma_f16_ss(tmem + s * 128, ptx::make_desc_kmajor_sw128(q_addr + off),
+                          ptx::make_desc_kmajor_sw128(k_addr + off), IDESC_QK, kk != 0);
+        }
+        ptx::tc_commit(&k_empty[s]);
+        ptx::tc_commit(&s_full[s]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(&v_full[s], ph);
+        ptx::mbar_wait(&o_empty[s], ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + s * TILE_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t a = ptx::make_desc_kmajor_sw128(p_addr + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
+          const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
+          ptx::mma_f16_ss(tmem + 256 + s * 128, a, b, IDESC_PV, kk != 0);
+        }
+        ptx::tc_commit(&v_empty[s]);
+        ptx::tc_commit(p_empty);
+        ptx::tc_commit(&o_full[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;                      // query row inside the tile
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float o[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) o[i] = 0.f;
+    uint8_t* p_row = smem + OFF_P + r * 128;
+    const int sw = r & 7;
+
+    auto accumulate = [&](int jt, float a) {
+      const int s = jt & 1;
+      ptx::mbar_wait(&o_full[s], (jt >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t t[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + 256 + s * 128 + c * 32, t);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(t[i]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&o_empty[s]);
+    };
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      ptx::mbar_wait(&s_full[s], (j >> 1) & 1);
+      ptx::tc_fence_after();
+      const int kv_left = Lk - j * BN;                  // columns >= kv_left are padding (zero-filled keys)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t t[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + c * 32, t);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = (c * 32 + i < kv_left) ? __uint_as_float(t[i]) : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = ex2f((m - m_new) * scale_log2);
+      const float mneg = -m_new * scale_log2;
+      ptx::mbar_wait(p_empty, (j & 1) ^ 1);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t t[32];
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + c * 32, t);
+        ptx::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < kv_left) ? ex2f(fmaf(__uint_as_float(t[i]), scale_log2, mneg)) : 0.f;
+          float p1 = (c * 32 + i + 1 < kv_left) ? ex2f(fmaf(__uint_as_float(t[i + 1]), scale_log2, mneg)) : 0.f;
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          // accumulate what the tensor core will actually see (bf16-rounded probabilities)
+          float2 hf = __bfloat1622float2(h);
+          sum += hf.x + hf.y;
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // 32 keys = 64 bytes = four 16-byte chunks of this row inside slice (c / 2)
+        uint8_t* base = p_row + (c >> 1) * SLICE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((c & 1) * 4 + q) ^ sw;
+          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+      }
+      l = l * alpha + sum;
+      m = m_new;
+      ptx::tc_fence_before();            // S_j fully read
+      ptx::fence_proxy_async_smem();     // P_j (generic-proxy stores) visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&s_empty[s]);
+        ptx::mbar_arrive(p_full);
+      }
+      if (j > 0) accumulate(j - 1, alpha_prev);
+      alpha_prev = alpha;
+    }
+    accumulate(n_kv - 1, alpha_prev);
+
+    const int q_row = q0 + r;
+    if (q_row < Lq) {
+      const float inv = 1.0f / l;
+      const int b = bh / H, h = bh - b * H;
+      __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {
+        uint4 u;
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
+        __nv_bfloat162 a1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
+        __nv_bfloat162 a2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv);
+        __nv_bfloat162 a3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
+        u.x = *reinterpret_cast<uint32_t*>(&a0);
+        u.y = *reinterpret_cast<uint32_t*>(&a1);
+        u.z = *reinterpret_cast<uint32_t*>(&a2);
+        u.w = *reinterpret_cast<uint32_t*>(&a3);
+        *reinterpret_cast<uint4*>(dst + i) = u;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<attn::TMEM_COLS>(tmem);
+  }
+}
+
+int attention_d128(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                   int H, int Lq, int Lk, float scale, cudaStream_t st) {
+  using namespace attn;
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[3] = {64, 128, 1};
+  {
+    uint64_t dims[3] = {128, (uint64_t)Lq, (uint64_t)B * H};
+    uint64_t str[3] = {2, 256, (uint64_t)Lq * 256};
+    if (make_tmap(&tq, q, 3, dims, str, box, 2)) return -20;
+  }
+  {
+    uint64_t dims[3] = {128, (uint64_t)Lk, (uint64_t)B * H};
+    uint64_t str[3] = {2, 256, (uint64_t)Lk * 256};
+    if (make_tmap(&tk, k, 3, dims, str, box, 2)) return -21;
+    if (make_tmap(&tv, v, 3, dims, str, box, 2)) return -22;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  dim3 grid((Lq + BM - 1) / BM, B * H);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  attention_d128_kernel<<<grid, 256, SMEM_BYTES, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H,
+                                                       Lq, Lk, scale_log2);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pa

@@ -1,0 +1,316 @@
+// Memory-bound glue kernels (bf16 I/O, fp32 math, 16-byte vector accesses):
+// LayerNorm + AdaLN modulate, sinusoidal timestep embedding, patchify (NCHW latent -> tokens, source may be a
+// peer GPU), SiLU/add, GroupNorm(+SiLU) NHWC, CFG + Euler update with (peer) store, cross-GPU flag words.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+
+namespace pa {
+
+static inline long long pa_min_ll(long long a, long long b) { return a < b ? a : b; }
+
+__device__ __forceinline__ float2 bf2f(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t f2bf(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&o)[8]) {
+  float2 a = bf2f(u.x), b = bf2f(u.y), c = bf2f(u.z), d = bf2f(u.w);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; o[4] = c.x; o[5] = c.y; o[6] = d.x; o[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  uint4 u;
+  u.x = f2bf(v[0], v[1]); u.y = f2bf(v[2], v[3]); u.z = f2bf(v[4], v[5]); u.w = f2bf(v[6], v[7]);
+  return u;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ LayerNorm + modulate
+// One warp per row; the row (D <= 8192) is held in registers between the statistics and the write pass.
+template <int MAX_VEC>   // MAX_VEC uint4 per lane: D <= 32*8*MAX_VEC
+__global__ void __launch_bounds__(256) ln_mod_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                     long long x_bs, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                     long long o_bs, const __nv_bfloat16* __restrict__ scale,
+                                                     const __nv_bfloat16* __restrict__ shift, long long mod_bs,
+                                                     const __nv_bfloat16* __restrict__ gamma,
+                                                     const __nv_bfloat16* __restrict__ beta, int batch, int rows, int D,
+                                                     float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * rows) return;
+  const int b = warp / rows, r = warp - b * rows;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + b * x_bs + static_cast<long long>(r) * ldx);
+  const int nvec = D >> 3;
+  uint4 buf[MAX_VEC];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      buf[i] = xr[idx];
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s += v[e]; ss += v[e] * v[e]; }
+    }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float mean = s / D;
+  const float var = fmaxf(ss / D - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + b * o_bs + static_cast<long long>(r) * ldo);
+  const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + b * mod_bs) : nullptr;
+  const uint4* sh = shift ? reinterpret_cast<const uint4*>(shift + b * mod_bs) : nullptr;
+  const uint4* ga = gamma ? reinterpret_cast<const uint4*>(gamma) : nullptr;
+  const uint4* be = beta ? reinterpret_cast<const uint4*>(beta) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd;
+      if (ga) {
+        float g[8];
+        unpack8(__ldg(ga + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= g[e];
+      }
+      if (be) {
+        float g[8];
+        unpack8(__ldg(be + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += g[e];
+      }
+      if (sc) {
+        float g[8];
+        unpack8(__ldg(sc + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= (1.0f + g[e]);
+      }
+      if (sh) {
+        float g[8];
+        unpack8(__ldg(sh + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += g[e];
+      }
+      orow[idx] = pack8(v);
+    }
+  }
+}
+
+int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,
+                       const void* scale, const void* shift, long long mod_bs, const void* gamma, const void* beta,
+                       int batch, int rows, int D, float eps, cudaStream_t st) {
+  if (D % 8 || ldx % 8 || ldo % 8 || x_bs % 8 || o_bs % 8 || mod_bs % 8) return -1;
+  const long long warps = static_cast<long long>(batch) * rows;
+  const int threads = 256;
+  const int blocks = static_cast<int>((warps * 32 + threads - 1) / threads);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto O = static_cast<__nv_bfloat16*>(out);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
+  auto G = static_cast<const __nv_bfloat16*>(gamma);
+  auto Bt = static_cast<const __nv_bfloat16*>(beta);
+  if (D <= 32 * 8 * 4)
+    ln_mod_kernel<4><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 12)
+    ln_mod_kernel<12><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 20)
+    ln_mod_kernel<20><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else
+    return -2;
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ timestep embedding
+__global__ void temb_kernel(const void* t, __nv_bfloat16* out, long long ldo, int B, int dim, float time_factor,
+                            float max_period, int t_is_bf16) {
+  const int b = blockIdx.x;
+  const int half = dim / 2;
+  float tv = t_is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(t)[b]) : static_cast<const float*>(t)[b];
+  tv *= time_factor;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float f = expf(-logf(max_period) * static_cast<float>(i) / static_cast<float>(half));
+    float sn, cs;
+    sincosf(tv * f, &sn, &cs);
+    out[b * ldo + i] = __float2bfloat16(cs);
+    out[b * ldo + half + i] = __float2bfloat16(sn);
+  }
+}
+
+int timestep_embedding(const void* t, void* out, long long ldo, int B, int dim, float time_factor, float max_period,
+                       int t_is_bf16, cudaStream_t st) {
+  temb_kernel<<<B, 128, 0, st>>>(t, static_cast<__nv_bfloat16*>(out), ldo, B, dim, time_factor, max_period, t_is_bf16);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ patchify (the unfused scatter path)
+// out[b, hh*Wp + ww, c*ps*ps + ph*ps + pw] = x[b, c, hh*ps+ph, ww*ps+pw];  x may be a peer mapping.
+__global__ void patchify_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, long long ldo,
+                                long long o_bs, int B, int C, int H, int W, int ps) {
+  const int Wp = W / ps, Hp = H / ps;
+  const long long total = static_cast<long long>(B) * C * H * (W / 2);   // pairs along W
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w2 = static_cast<int>(i % (W / 2));
+    long long r = i / (W / 2);
+    const int h = static_cast<int>(r % H);
+    r /= H;
+    const int c = static_cast<int>(r % C);
+    const int b = static_cast<int>(r / C);
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(x + ((static_cast<long long>(b) * C + c) * H + h) * W + w2 * 2);
+    const int hh = h / ps, ph = h % ps;
+    if (ps == 2) {
+      const int ww = w2;
+      __nv_bfloat16* o = out + b * o_bs + static_cast<long long>(hh * Wp + ww) * ldo + c * 4 + ph * 2;
+      *reinterpret_cast<uint32_t*>(o) = v;
+    } else {
+      const __nv_bfloat16* pv = reinterpret_cast<const __nv_bfloat16*>(&v);
+      for (int e = 0; e < 2; ++e) {
+        const int w = w2 * 2 + e, ww = w / ps, pw = w % ps;
+        out[b * o_bs + static_cast<long long>(hh * Wp + ww) * ldo + (c * ps + ph) * ps + pw] = pv[e];
+      }
+    }
+  }
+  (void)Hp;
+}
+
+int patchify(const void* x, void* out, long long ldo, long long o_bs, int B, int C, int H, int W, int ps,
+             cudaStream_t st) {
+  if (W % 2) return -1;
+  const long long total = static_cast<long long>(B) * C * H * (W / 2);
+  const int blocks = static_cast<int>(pa_min_ll((total + 255) / 256, 148 * 8));
+  patchify_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), ldo,
+                                          o_bs, B, C, H, W, ps);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ small elementwise
+__global__ void silu_kernel(const uint4* x, uint4* out, long long nvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v[8];
+    unpack8(x[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = v[e] / (1.0f + __expf(-v[e]));
+    out[i] = pack8(v);
+  }
+}
+int silu_bf16(const void* x, void* out, long long n, cudaStream_t st) {
+  if (n % 8) return -1;
+  const long long nv = n / 8;
+  silu_kernel<<<static_cast<int>(pa_min_ll((nv + 255) / 256, 148 * 8)), 256, 0, st>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(out), nv);
+  return (int)cudaGetLastError();
+}
+
+__global__ void add_kernel(const uint4* a, const uint4* b, uint4* out, long long nvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(a[i], x);
+    unpack8(b[i], y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    out[i] = pack8(x);
+  }
+}
+int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st) {
+  if (n % 8) return -1;
+  const long long nv = n / 8;
+  add_kernel<<<static_cast<int>(pa_min_ll((nv + 255) / 256, 148 * 8)), 256, 0, st>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), nv);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ CFG + Euler + (peer) store
+// mode 0: x_out = eps (passthrough)        mode 1: x_out = x + (s' - s) * d,  d = u + cfg*(c - u)
+// (flow / v-prediction "CONST" parameterisation);  mode 2: eps-prediction Euler: d = eps,
+// x_out = x + (s' - s) * d as well (k-diffusion's to_d(x, sigma, x - sigma*eps) == eps).
+__global__ void cfg_euler_kernel(const uint4* __restrict__ x, const uint4* __restrict__ ec, const uint4* __restrict__ eu,
+                                 uint4* __restrict__ xo, const float* __restrict__ sigmas, float cfg,
+                                 long long nvec_per_sample, int batch, long long out_vec_off, int mode) {
+  const long long total = nvec_per_sample * batch;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / nvec_per_sample);
+    float d[8];
+    unpack8(ec[i], d);
+    if (eu != nullptr) {
+      float u[8];
+      unpack8(eu[i], u);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = u[e] + cfg * (d[e] - u[e]);
+    }
+    if (mode != 0) {
+      const float dt = sigmas[2 * b + 1] - sigmas[2 * b];
+      float xv[8];
+      unpack8(x[i], xv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = xv[e] + dt * d[e];
+    }
+    xo[out_vec_off + i] = pack8(d);
+  }
+}
+
+int cfg_euler_store(const void* x, const void* ec, const void* eu, void* x_out, const void* sigmas, float cfg,
+                    long long n_per_sample, int batch, long long out_sample_off, int mode, cudaStream_t st) {
+  if (n_per_sample % 8) return -1;
+  const long long nv = n_per_sample / 8;
+  const long long total = nv * batch;
+  cfg_euler_kernel<<<static_cast<int>(pa_min_ll((total + 255) / 256, 148 * 8)), 256, 0, st>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(ec), static_cast<const uint4*>(eu),
+      static_cast<uint4*>(x_out), static_cast<const float*>(sigmas), cfg, nv, batch, out_sample_off * nv, mode);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ cross-GPU flags
+// signal: write `value` into slot `slot` of every peer's flag array (release at system scope, after all
+// prior writes of this stream are visible).  wait: spin (acquire) until flags[first..first+n) >= value,
+// bounded by a cycle budget -> sets *error_word instead of hanging.
+__global__ void signal_kernel(uint32_t* const* peers, int n_peers, int slot, uint32_t value) {
+  __threadfence_system();
+  const int i = threadIdx.x;
+  if (i < n_peers) ptx::st_release_sys_u32(peers[i] + slot, value);
+}
+
+__global__ void wait_kernel(const uint32_t* flags, int first, int n, uint32_t value, long long timeout,
+                            uint32_t* err) {
+  const int i = threadIdx.x;
+  if (i < n) {
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ptx::ld_acquire_sys_u32(flags + first + i) - value) < 0) {
+      if (clock64() - t0 > timeout) {
+        if (err) atomicExch(err, 0xDEAD0000u | static_cast<uint32_t>(first + i));
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __threadfence_system();
+}
+
+int signal_flags(uint32_t* const* peer_flag_ptrs, int n_peers, int slot, uint32_t value, cudaStream_t st) {
+  signal_kernel<<<1, 32, 0, st>>>(peer_flag_ptrs, n_peers, slot, value);
+  return (int)cudaGetLastError();
+}
+
+int wait_flags(const uint32_t* flags, int first, int n, uint32_t value, long long timeout, uint32_t* err,
+               cudaStream_t st) {
+  wait_kernel<<<1, 32, 0, st>>>(flags, first, n, value, timeout, err);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace pa

@@ -1,0 +1,119 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction + launch.
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <mutex>
+
+#include "../common/host.h"
+#include "gemm_tcgen05.cuh"
+
+namespace pa {
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// rank-N bf16/u8 tensor map with 128-byte swizzle.  dims/strides innermost first; strides[0] is implicit.
+int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int elem_bytes) {
+  auto fn = encode_fn();
+  if (!fn) return -1;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i];
+  }
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUresult r = fn(out, dt, rank, const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[pa] cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u)\n", (int)r, rank,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return -2;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+  return n[dev];
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+// A: [batch, rows, K] with row stride lda and batch stride a_bstride (elements); W: [N, K] row stride ldw.
+int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, GemmParams p,
+              int force_bn, cudaStream_t st) {
+  if (p.K % 8 || lda % 8 || ldw % 8 || a_bstride % 8) return -10;   // TMA: 16-byte strides
+  if (p.N % 32) return -11;
+  const int m_tiles = ((p.rows + 127) / 128) * p.batch;
+  int bn = force_bn;
+  if (bn == 0) {
+    if (p.mode == EPI_QKV_ROPE) {
+      bn = 256;
+    } else if (p.N <= 64) {
+      bn = 64;
+    } else {
+      bn = 64;
+      const int cands[3] = {256, 128, 64};
+      for (int c : cands) {
+        if (p.N % c && p.N > c) continue;
+        if (m_tiles * ((p.N + c - 1) / c) >= num_sms()) { bn = c; break; }
+      }
+    }
+  }
+  if (p.mode == EPI_QKV_ROPE && bn < 128) return -12;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
+    uint64_t str[3] = {2, (uint64_t)lda * 2, (uint64_t)(p.batch > 1 ? a_bstride : (long long)p.rows * lda) * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if (make_tmap(&ta, A, 3, dims, str, box, 2)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (make_tmap(&tb, W, 2, dims, str, box, 2)) return -21;
+  }
+  const int tiles = m_tiles * ((p.N + bn - 1) / bn);
+  switch (bn) {
+    case 256: return launch<256>(ta, tb, p, tiles, st);
+    case 128: return launch<128>(ta, tb, p, tiles, st);
+    case 64: return launch<64>(ta, tb, p, tiles, st);
+  }
+  return -13;
+}
+
+}  // namespace pa

@@ -1,0 +1,48 @@
+// GEMM epilogue modes + parameter block shared by device code and the host binding.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace pa {
+
+enum EpiMode : int {
+  EPI_BIAS = 0,
+  EPI_BIAS_GELU = 1,
+  EPI_BIAS_SILU = 2,
+  EPI_GATE_RES = 3,     // out = residual + gate[b, n] * (acc + bias)
+  EPI_QKV_ROPE = 4,     // N = 3*H*128 (+ mlp columns when mlp_cols > 0)
+  EPI_EULER_UNPATCH = 5,// N = C*ps*ps : velocity -> x_next written in NCHW, possibly to a peer
+  EPI_GEGLU = 6,        // W rows interleaved [a(32) | g(32)]...: out[:, n/2] = a * gelu(g)
+  EPI_RES = 7,          // out = residual + acc + bias
+};
+
+struct GemmParams {
+  int rows;          // rows per batch
+  int batch;
+  int N, K;
+  int mode;
+  // generic output
+  __nv_bfloat16* out;
+  long long ldc, out_bstride;
+  const __nv_bfloat16* bias;        // [N] or nullptr
+  const __nv_bfloat16* residual;    // EPI_GATE_RES / EPI_RES
+  long long ldr, res_bstride;
+  const __nv_bfloat16* gate;        // [batch, N] with stride gate_bstride
+  long long gate_bstride;
+  // QKV
+  __nv_bfloat16 *q, *k, *v;         // [batch, H, seq_total, 128]
+  const __nv_bfloat16 *q_scale, *k_scale;   // [128] RMSNorm weights
+  const float2* rope;               // [seq_total, 64] (cos, sin); nullptr = no rope
+  int heads, seq_off, seq_total;
+  int mlp_cols;                     // columns after the 3*H*128 qkv columns (FLUX single blocks)
+  long long mlp_col_off;            // where they start inside `out`
+  float qk_eps;
+  // Euler / unpatchify epilogue (the fused "gather")
+  const __nv_bfloat16* x_in;        // local latent shard  [batch, C, Hl, Wl]
+  __nv_bfloat16* x_out;             // destination (lead GPU buffer, possibly a peer mapping)
+  long long xout_sample_off;        // first sample of this rank inside x_out
+  const float* sigmas;              // [batch, 2] (sigma, sigma_next) per sample, or nullptr => out = v
+  int C, Hl, Wl, ps;
+};
+
+}  // namespace pa
