@@ -47,6 +47,8 @@ class FluxExecutor(nn.Module):
             raise ValueError("FluxExecutor is specialised for 2x2 patches")
         self.mlp = int(p.hidden_size * p.mlp_ratio)
         self.cuda_graphs = cuda_graphs
+        # the fused scatter/patch-embed kernel is specialised for 16 latent channels x (2x2) patches
+        self.fused_embed = (p.in_channels == 64)
         d = self.device
         W: Dict[str, torch.Tensor] = {}
 
@@ -149,7 +151,7 @@ class FluxExecutor(nn.Module):
         return ws["MOD"][:, off:off + self.hid]
 
     def _run(self, ws, x_ptr: int, t, ctx, y, guidance, out, x_in=None, sigmas=None, out_ptr: Optional[int] = None,
-             out_sample_off: int = 0):
+             out_sample_off: int = 0, t_ptr: Optional[int] = None, g_ptr: Optional[int] = None, x_copy=None):
         W, hid, mlp, Lt, B = self.W, self.hid, self.mlp, ws["Lt"], ws["B"]
         C = ops.require()
         n = 0
@@ -159,19 +161,31 @@ class FluxExecutor(nn.Module):
         ATT = CAT[:, :, :hid]
         MH = CAT[:, :, hid:]
         # ---- embedders
-        C.patchify(x_ptr, ws["TOK"], B, self.params.in_channels // 4, ws["H"], ws["Wd"], 2)
-        ops.gemm(ws["TOK"], W["img_in.w"], "bias", out=Xi, bias=W["img_in.b"])
-        ops.gemm(ctx, W["txt_in.w"], "bias", out=Xt, bias=W["txt_in.b"])
         HC = ws["HC"]
-        ops.timestep_embedding(t, 256, out=ws["T1"])
+        ge = self.params.guidance_embed
+        if self.fused_embed:
+            # fused scatter: (peer) latent shard -> patchify -> img_in GEMM, + timestep/guidance embeddings
+            C.scatter_patch_embed(W["img_in.w"], W["img_in.b"], x_ptr, t_ptr if t_ptr is not None else t.data_ptr(),
+                                  (g_ptr if g_ptr is not None else guidance.data_ptr()) if ge else 0, ws["T1"],
+                                  ws["T2"] if ge else None, x_copy, Xi, self.params.in_channels // 4, ws["H"],
+                                  ws["Wd"], 1000.0)
+            n += 1
+        else:
+            C.patchify(x_ptr, ws["TOK"], B, self.params.in_channels // 4, ws["H"], ws["Wd"], 2)
+            ops.gemm(ws["TOK"], W["img_in.w"], "bias", out=Xi, bias=W["img_in.b"])
+            ops.timestep_embedding(t, 256, out=ws["T1"])
+            n += 3
+            if ge:
+                ops.timestep_embedding(guidance, 256, out=ws["T2"])
+                n += 1
+        ops.gemm(ctx, W["txt_in.w"], "bias", out=Xt, bias=W["txt_in.b"])
         ops.gemm(ws["T1"], W["time_in.in.w"], "silu", out=HC[:, :hid], bias=W["time_in.in.b"])
         col = hid
-        n += 5
-        if self.params.guidance_embed:
-            ops.timestep_embedding(guidance, 256, out=ws["T2"])
+        n += 2
+        if ge:
             ops.gemm(ws["T2"], W["guidance_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["guidance_in.in.b"])
             col += hid
-            n += 2
+            n += 1
         ops.gemm(y, W["vector_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["vector_in.in.b"])
         ops.gemm(HC, W["vec_out.w"], "silu", out=ws["SVEC"], bias=W["vec_out.b"])          # silu(vec)
         ops.gemm(ws["SVEC"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])            # all modulations
@@ -248,16 +262,19 @@ class FluxExecutor(nn.Module):
 
     @torch.no_grad()
     def denoise_step(self, x, timesteps, context, y, guidance, sigmas, out=None, out_ptr=None, out_sample_off=0,
-                     x_src_ptr: Optional[int] = None):
+                     x_src_ptr: Optional[int] = None, t_src_ptr: Optional[int] = None,
+                     g_src_ptr: Optional[int] = None):
         """Model forward + Euler update ``x + (sigma_next - sigma) * v`` fused into the last GEMM's
         epilogue; the result may be stored straight into a peer GPU's buffer (``out_ptr``).
-        ``x_src_ptr`` lets the first kernel pull the latent shard from a peer mapping."""
+        ``x_src_ptr`` / ``t_src_ptr`` / ``g_src_ptr`` let the first kernel pull the latent shard and the
+        per-sample scalars from a peer mapping (then ``x`` is filled with a local copy as a side effect)."""
         with torch.cuda.device(self.device):
             ws = self.workspace(x.shape[0], x.shape[2], x.shape[3], context.shape[1])
             if out is None and out_ptr is None:
                 out = ws["OUT"]
             self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, y, guidance, out,
-                      x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off)
+                      x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
+                      g_ptr=g_src_ptr, x_copy=x if (x_src_ptr is not None and self.fused_embed) else None)
             return out
 
 

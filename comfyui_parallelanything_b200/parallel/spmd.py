@@ -142,12 +142,23 @@ class SpmdFluxEngine:
         self.loc = dict(x=e(n, self.C, self.H, self.W), t=e(n), ctx=e(n, txt_len, p.context_in_dim),
                         y=e(n, p.vec_in_dim), g=e(n), sig=e(n, 2, dt=torch.float32))
         self.comm_launches = 0
+        self.tma_peer = os.environ.get("PA_TMA_PEER", "1") != "0"
         log.info("SPMD rank %d/%d: samples [%d, %d) of %d, backend=%s", self.rank, self.world, self.off_local,
                  self.off_local + self.n_local, B, backend)
 
     # -------------------------------------------------------------- helpers
     def _src(self, name: str, row_bytes: int) -> int:
         return self.heap.peer_ptr(0, self.off[name]) + self.off_local * row_bytes
+
+    def _peer_view(self, name: str) -> torch.Tensor:
+        """This rank's shard of rank 0's staging tensor as a (peer-mapped) torch view."""
+        shape, dt = self.spec[name]
+        row = 1
+        for s_ in shape[1:]:
+            row *= s_
+        row_bytes = row * torch.empty((), dtype=dt).element_size()
+        t = self.heap.C.tensor_from_ptr(self._src(name, row_bytes), row_bytes * self.n_local, self.dev.index)
+        return t.view(dt).view(self.n_local, *shape[1:])
 
     def _pull(self, name: str) -> None:
         """Shard of a small tensor: peer -> local with a device-side copy (cudaMemcpyAsync P2P)."""
@@ -184,17 +195,26 @@ class SpmdFluxEngine:
             if self.rank == 0:
                 loc = {k: self.buf[k][self.off_local:self.off_local + self.n_local] for k in ("x", "t", "ctx", "y", "g", "sig")}
             else:
-                for name in ("x", "t", "ctx", "y", "g", "sig"):
-                    self._pull(name)
-                    n += 1
                 loc = {k: v[:self.n_local] for k, v in self.loc.items()}
+                if self.tma_peer:
+                    # conditioning / pooled vector are consumed by TMA directly from the lead's HBM
+                    # (A operand of txt_in / vector_in over NVLink); only the 8-byte sigmas are copied
+                    self._pull("sig")
+                    n += 1
+                    loc["ctx"] = self._peer_view("ctx")
+                    loc["y"] = self._peer_view("y")
+                else:
+                    for name in ("ctx", "y", "sig"):
+                        self._pull(name)
+                        n += 1
             x_bytes = self.C * self.H * self.W * 2
             # fused scatter: the patchify/embed kernel loads this rank's latent shard directly from
             # rank 0's buffer over NVLink; fused gather: the last GEMM epilogue stores x_{t-1} rows at
             # their final offset in rank 0's output buffer.
             self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"],
                                  out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
-                                 x_src_ptr=self._src("x", x_bytes))
+                                 x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2),
+                                 g_src_ptr=self._src("g", 2))
             n += self.ex.launches_per_step
         C.signal_flags(self.lead_flag_table, 1, self.FLAG_DONE0 + self.rank, e)
         n += 1

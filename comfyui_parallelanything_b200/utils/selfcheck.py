@@ -342,3 +342,27 @@ def flux_executor_mid():
         got = ex(**inp)
         want = oracle(**{k: v.float() for k, v in inp.items()})
     return _cmp("flux_executor_mid", got, want, 0.03)
+
+
+@check
+def scatter_patch_embed():
+    """Fused scatter kernel on one GPU (source pointers are local): patchify + img_in + temb."""
+    from ..models import flux
+    C_ = ops.require()
+    n, Cc, Hl, Wl, N = 2, 16, 48, 40, 512
+    Li = (Hl // 2) * (Wl // 2)
+    x, w, b = _rand(n, Cc, Hl, Wl), _rand(N, 64, scale=0.1), _rand(N)
+    t = torch.tensor([0.3, 0.9], device=_dev(), dtype=torch.bfloat16)
+    g = torch.tensor([3.5, 1.0], device=_dev(), dtype=torch.bfloat16)
+    X = torch.zeros(n, 77 + Li, N, dtype=torch.bfloat16, device=_dev())
+    t_emb, g_emb = torch.zeros(n, 256, dtype=torch.bfloat16, device=_dev()), torch.zeros(n, 256, dtype=torch.bfloat16, device=_dev())
+    xc = torch.zeros_like(x)
+    C_.scatter_patch_embed(w, b, x.data_ptr(), t.data_ptr(), g.data_ptr(), t_emb, g_emb, xc, X[:, 77:], Cc, Hl, Wl, 1000.0)
+    m = flux.Flux.__new__(flux.Flux)
+    m.patch_size = 2
+    want = _gemm_ref(flux.Flux.patchify(m, x), w, b)
+    r = _cmp("scatter_patch_embed", X[:, 77:], want, 0.012)
+    r2 = _cmp("temb", torch.cat([t_emb, g_emb]), torch.cat([flux.timestep_embedding(t, 256), flux.timestep_embedding(g, 256)]), 0.01)
+    r["temb_mean_rel"] = r2["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"] and bool(torch.equal(xc, x)) and bool(X[:, :77].abs().max().item() == 0)
+    return r

@@ -5,6 +5,7 @@
 #include <torch/extension.h>
 
 #include "common/host.h"
+#include "comm/scatter_params.h"
 #include "kernels/gemm_params.h"
 #include "runtime/runtime.h"
 
@@ -153,6 +154,31 @@ static void patchify(uintptr_t x_ptr, Tensor out, int B, int C, int H, int W, in
         "patchify");
 }
 
+// Fused scatter: peer latent shard -> patchify -> img_in GEMM (+ bias) -> X[:, Lt:], plus the
+// sinusoidal embeddings of the shard's timesteps / guidance values (read from the peer).
+static void scatter_patch_embed(Tensor W, Tensor bias, uintptr_t x_src, uintptr_t t_src, uintptr_t g_src, Tensor t_emb,
+                                c10::optional<Tensor> g_emb, c10::optional<Tensor> x_copy, Tensor out, int C, int Hl,
+                                int Wl, double time_factor) {
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(W.dim() == 2 && W.size(1) == 64 && W.stride(1) == 1, "img_in weight must be [N, 64]");
+  pa::ScatterEmbedParams p{};
+  int ob, orows;
+  view3(out, ob, orows, p.ldo, p.out_bstride);
+  p.x_src = reinterpret_cast<const __nv_bfloat16*>(x_src);
+  p.t_src = reinterpret_cast<const __nv_bfloat16*>(t_src);
+  p.g_src = reinterpret_cast<const __nv_bfloat16*>(g_src);
+  p.t_emb = reinterpret_cast<__nv_bfloat16*>(t_emb.data_ptr());
+  p.g_emb = g_emb ? reinterpret_cast<__nv_bfloat16*>(g_emb->data_ptr()) : nullptr;
+  TORCH_CHECK(p.g_src == nullptr || p.g_emb != nullptr, "g_emb required with g_src");
+  p.x_copy = x_copy ? reinterpret_cast<__nv_bfloat16*>(x_copy->data_ptr()) : nullptr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias.data_ptr());
+  p.n = ob; p.C = C; p.Hl = Hl; p.Wl = Wl; p.N = (int)W.size(0); p.Li = orows;
+  TORCH_CHECK(p.Li == (Hl / 2) * (Wl / 2), "out rows must equal the number of 2x2 patches");
+  p.time_factor = (float)time_factor;
+  check(pa::scatter_patch_embed(W.data_ptr(), W.stride(0), p, cur_stream()), "scatter_patch_embed");
+}
+
 static void silu_(Tensor x, Tensor out) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && out.is_contiguous());
@@ -218,6 +244,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("eps") = 1e-6);
   m.def("timestep_embedding", &timestep_embedding);
   m.def("patchify", &patchify);
+  m.def("scatter_patch_embed", &scatter_patch_embed);
   m.def("silu", &silu_);
   m.def("add", &add_);
   m.def("attention", &attention);

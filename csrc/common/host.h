@@ -8,6 +8,8 @@
 namespace pa {
 
 struct GemmParams;
+struct ScatterEmbedParams;
+int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& p, cudaStream_t st);
 
 int num_sms();
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Run every native-kernel self-check on the current GPU, one process per check (a
-trapped/hung kernel cannot poison the rest), and write ``gpurun_out/selfcheck.json``.
+"""Run every native-kernel self-check on the current GPU and write ``gpurun_out/selfcheck.json``.
+
+Checks run sequentially in a child process; if a kernel traps (poisoned CUDA context) or hangs past
+the timeout, the child is killed and a fresh one continues with the next check — one bad kernel
+cannot hide the state of the rest.
 
     python tools/gpu_check.py                 # all checks
     python tools/gpu_check.py --only gemm     # substring filter
-    python tools/gpu_check.py --check NAME    # (internal) run one check in-process
 """
 from __future__ import annotations
 
@@ -19,50 +21,70 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run_one(name: str) -> int:
+def child(names) -> int:
     import torch
     from comfyui_parallelanything_b200.utils import selfcheck
-    t0 = time.time()
-    try:
-        r = selfcheck.CHECKS[name]()
-        torch.cuda.synchronize()
-    except Exception as e:  # noqa: BLE001
-        r = dict(name=name, ok=False, error=f"{type(e).__name__}: {e}"[:500])
-    r["seconds"] = round(time.time() - t0, 2)
-    print("PA_CHECK " + json.dumps(r), flush=True)
-    return 0 if r.get("ok") else 1
+    for name in names:
+        print("PA_START " + name, flush=True)
+        t0 = time.time()
+        fatal = False
+        try:
+            r = selfcheck.CHECKS[name]()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            msg = f"{type(e).__name__}: {e}"
+            r = dict(name=name, ok=False, error=msg[:600])
+            fatal = "CUDA" in msg or "cuda" in msg or "launch failure" in msg
+        r["seconds"] = round(time.time() - t0, 2)
+        print("PA_CHECK " + json.dumps(r), flush=True)
+        if fatal:
+            return 3          # context is gone: let the parent restart us
+    return 0
 
 
 def main() -> int:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--check")
+    ap.add_argument("--child", nargs="*")
     ap.add_argument("--only", default="")
-    ap.add_argument("--timeout", type=int, default=180)
+    ap.add_argument("--timeout", type=int, default=240, help="per-child wall clock limit (s)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "selfcheck.json"))
     a = ap.parse_args()
-    if a.check:
-        return run_one(a.check)
+    if a.child is not None:
+        return child(a.child)
     from comfyui_parallelanything_b200.utils import selfcheck
-    names = [n for n in selfcheck.CHECKS if a.only in n]
-    results = []
-    for n in names:
+    todo = [n for n in selfcheck.CHECKS if a.only in n]
+    results = {}
+    while todo:
+        p = subprocess.Popen([sys.executable, __file__, "--child"] + todo, stdout=subprocess.PIPE,
+                             stderr=subprocess.PIPE, text=True)
         try:
-            p = subprocess.run([sys.executable, __file__, "--check", n], capture_output=True, text=True,
-                               timeout=a.timeout)
-            line = [l for l in p.stdout.splitlines() if l.startswith("PA_CHECK ")]
-            if line:
-                r = json.loads(line[-1][len("PA_CHECK "):])
-            else:
-                r = dict(name=n, ok=False, error="no result", stdout=p.stdout[-800:], stderr=p.stderr[-1500:])
+            out, err = p.communicate(timeout=a.timeout)
         except subprocess.TimeoutExpired:
-            r = dict(name=n, ok=False, error=f"timeout after {a.timeout}s")
-        results.append(r)
+            p.kill()
+            out, err = p.communicate()
+            err += "\n[gpu_check] child timed out"
+        started = [l.split(" ", 1)[1] for l in out.splitlines() if l.startswith("PA_START ")]
+        for l in out.splitlines():
+            if l.startswith("PA_CHECK "):
+                r = json.loads(l[len("PA_CHECK "):])
+                results[r["name"] if r["name"] in todo else started[len(results) % max(1, len(started))]] = r
+        done = [n for n in started if any(r is results.get(n) for r in [results.get(n)]) and n in results]
+        if started and started[-1] not in results:       # died inside this check
+            results[started[-1]] = dict(name=started[-1], ok=False, error="child died/timed out",
+                                        stderr=err[-1500:])
+            done.append(started[-1])
+        if not started:
+            results[todo[0]] = dict(name=todo[0], ok=False, error="child produced no output", stderr=err[-1500:])
+            done.append(todo[0])
+        todo = [n for n in todo if n not in done and n not in results]
+    ordered = [results[n] for n in selfcheck.CHECKS if n in results]
+    for r in ordered:
         print(("PASS " if r.get("ok") else "FAIL ") + json.dumps(r), flush=True)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
-        json.dump(results, f, indent=1)
-    bad = [r["name"] for r in results if not r.get("ok")]
-    print(f"{len(results) - len(bad)}/{len(results)} checks passed; failed: {bad}")
+        json.dump(ordered, f, indent=1)
+    bad = [r["name"] for r in ordered if not r.get("ok")]
+    print(f"{len(ordered) - len(bad)}/{len(ordered)} checks passed; failed: {bad}")
     return 1 if bad else 0
 
 
