@@ -5,9 +5,11 @@
 //   warp 0   TMA producer: Q once, then K_j / V_j tiles (128 keys) through 2-stage rings
 //   warp 1   tcgen05.mma issuer:  S_j = Q K_j^T  (TMEM, double buffered)  and  O_j = P_j V_j (TMEM, double buffered)
 //   warp 2   TMEM allocator
-//   warps 4-7  softmax: thread == query row.  Two passes over S_j in TMEM (row max, then exp2 + row sum),
-//            P_j written to shared memory as a 128B-swizzled K-major A operand, running output kept in
-//            registers: O = O * alpha_j + O_j.
+//   warps 4-7  softmax: thread == query row.  S_j is read from TMEM once (128 registers), row max with
+//            3-input FMNMX, exp2 with packed FFMA2/FADD2, P_j written to shared memory as a 128B-swizzled
+//            K-major A operand.  O accumulates IN TMEM across all KV tiles (tcgen05.mma accumulate);
+//            it is only rescaled (tcgen05.ld -> mul -> tcgen05.st) when the running row max grows by
+//            more than 2^8 ("lazy rescaling"), which after the first tiles practically never happens.
 // V is consumed as an MN-major B operand straight from its natural [keys, d] layout (no transpose).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -34,6 +36,30 @@ __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -77,7 +103,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&s_empty[i], 4);
       ptx::mbar_init(&o_full[i], 1);
-      ptx::mbar_init(&o_empty[i], 4);
+      ptx::mbar_init(&o_empty[i], 4);      // (unused since O accumulates in TMEM)
     }
     ptx::mbar_init(p_full, 4);
     ptx::mbar_init(p_empty, 1);
@@ -138,84 +164,101 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const uint32_t ph = (j >> 1) & 1;
         ptx::mbar_wait(p_full, j & 1);
         ptx::mbar_wait(&v_full[s], ph);
-        ptx::mbar_wait(&o_empty[s], ph ^ 1);
         ptx::tc_fence_after();
         const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + s * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t a = ptx::make_desc_kmajor_sw128(p_addr + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
           const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
-          ptx::mma_f16_ss(tmem + 256 + s * 128, a, b, IDESC_PV, kk != 0);
+          ptx::mma_f16_ss(tmem + 256, a, b, IDESC_PV, (j | kk) != 0);
         }
         ptx::tc_commit(&v_empty[s]);
         ptx::tc_commit(p_empty);
-        ptx::tc_commit(&o_full[s]);
+        ptx::tc_commit(&o_full[0]);          // phase j & 1: "O includes tiles 0..j"
       }
     }
   } else if (warp >= 4) {
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;                      // query row inside the tile
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[128];
-#pragma unroll
-    for (int i = 0; i < 128; ++i) o[i] = 0.f;
+    const uint32_t o_addr = lane_addr + 256;
+    float m_used = -INFINITY, l = 0.f;
     uint8_t* p_row = smem + OFF_P + r * 128;
     const int sw = r & 7;
-
-    auto accumulate = [&](int jt, float a) {
-      const int s = jt & 1;
-      ptx::mbar_wait(&o_full[s], (jt >> 1) & 1);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + 256 + s * 128 + c * 32, t);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(t[i]);
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&o_empty[s]);
-    };
+    const unsigned long long sl2 = pack2(scale_log2, scale_log2);
 
     for (int j = 0; j < n_kv; ++j) {
       const int s = j & 1;
       ptx::mbar_wait(&s_full[s], (j >> 1) & 1);
       ptx::tc_fence_after();
-      const int kv_left = Lk - j * BN;                  // columns >= kv_left are padding (zero-filled keys)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + c * 32, t);
+      uint32_t sv[128];
+      {
+        uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        uint32_t(&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
+        uint32_t(&c3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128, c0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 32, c1);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 64, c2);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 96, c3);
         ptx::tmem_ld_wait();
+      }
+      // S_j is in registers: hand the TMEM buffer back so QK^T of tile j+2 can start
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
+
+      const int kv_left = Lk - j * BN;                  // < 128 only on a ragged last tile
+      if (kv_left < BN) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (c * 32 + i < kv_left) ? __uint_as_float(t[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) sv[i] = 0xff800000u;        // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_used));
+      const bool need = (m_new - m_used) * scale_log2 > 8.0f;      // always true on the first tile
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2f((m_used - m_new) * scale_log2) : 1.0f;
+        if (need) m_used = m_new;
+        l *= alpha;
+        if (j > 0) {                                    // O currently holds tiles 0..j-1
+          ptx::mbar_wait(&o_full[0], (j - 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t t[32];
+            ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            ptx::tmem_st_32x32b_x32(o_addr + c * 32, t);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2f((m - m_new) * scale_log2);
-      const float mneg = -m_new * scale_log2;
-      ptx::mbar_wait(p_empty, (j & 1) ^ 1);
-      float sum = 0.f;
-#pragma unroll 1
+      const float mneg_f = -m_used * scale_log2;
+      const unsigned long long mneg = pack2(mneg_f, mneg_f);
+      ptx::mbar_wait(p_empty, (j & 1) ^ 1);             // PV of tile j-1 has consumed the P buffer
+      unsigned long long sum2 = pack2(0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t t[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + c * 32, t);
-        ptx::tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < kv_left) ? ex2f(fmaf(__uint_as_float(t[i]), scale_log2, mneg)) : 0.f;
-          float p1 = (c * 32 + i + 1 < kv_left) ? ex2f(fmaf(__uint_as_float(t[i + 1]), scale_log2, mneg)) : 0.f;
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          // accumulate what the tensor core will actually see (bf16-rounded probabilities)
-          float2 hf = __bfloat1622float2(h);
-          sum += hf.x + hf.y;
+          float a0, a1;
+          unpack2(fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg), a0, a1);
+          a0 = ex2f(a0);
+          a1 = ex2f(a1);
+          sum2 = add2(sum2, pack2(a0, a1));
+          __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
         // 32 keys = 64 bytes = four 16-byte chunks of this row inside slice (c / 2)
@@ -226,37 +269,40 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
-      l = l * alpha + sum;
-      m = m_new;
-      ptx::tc_fence_before();            // S_j fully read
+      float s0, s1;
+      unpack2(sum2, s0, s1);
+      l += s0 + s1;
       ptx::fence_proxy_async_smem();     // P_j (generic-proxy stores) visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        ptx::mbar_arrive(&s_empty[s]);
-        ptx::mbar_arrive(p_full);
-      }
-      if (j > 0) accumulate(j - 1, alpha_prev);
-      alpha_prev = alpha;
+      if (lane == 0) ptx::mbar_arrive(p_full);
     }
-    accumulate(n_kv - 1, alpha_prev);
 
+    // ---- epilogue: O / l -> bf16
+    ptx::mbar_wait(&o_full[0], (n_kv - 1) & 1);
+    ptx::tc_fence_after();
     const int q_row = q0 + r;
-    if (q_row < Lq) {
-      const float inv = 1.0f / l;
-      const int b = bh / H, h = bh - b * H;
-      __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+    const float inv = 1.0f / l;
+    const int b = bh / H, h = bh - b * H;
+    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t t[32];
+      ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
+      ptx::tmem_ld_wait();
+      if (q_row < Lq) {
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
-        uint4 u;
-        __nv_bfloat162 a0 = __floats2bfloat162_rn(o[i] * inv, o[i + 1] * inv);
-        __nv_bfloat162 a1 = __floats2bfloat162_rn(o[i + 2] * inv, o[i + 3] * inv);
-        __nv_bfloat162 a2 = __floats2bfloat162_rn(o[i + 4] * inv, o[i + 5] * inv);
-        __nv_bfloat162 a3 = __floats2bfloat162_rn(o[i + 6] * inv, o[i + 7] * inv);
-        u.x = *reinterpret_cast<uint32_t*>(&a0);
-        u.y = *reinterpret_cast<uint32_t*>(&a1);
-        u.z = *reinterpret_cast<uint32_t*>(&a2);
-        u.w = *reinterpret_cast<uint32_t*>(&a3);
-        *reinterpret_cast<uint4*>(dst + i) = u;
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(t[i]) * inv, __uint_as_float(t[i + 1]) * inv);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
+          u.x = *reinterpret_cast<uint32_t*>(&a0);
+          u.y = *reinterpret_cast<uint32_t*>(&a1);
+          u.z = *reinterpret_cast<uint32_t*>(&a2);
+          u.w = *reinterpret_cast<uint32_t*>(&a3);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+        }
       }
     }
   }
