@@ -49,7 +49,7 @@ def native_ok(device) -> bool:
 
 
 EPI = {
-    "bias": 0, "gelu": 1, "silu": 2, "gate_res": 3, "qkv_rope": 4, "euler_unpatch": 5, "geglu": 6, "res": 7,
+    "bias": 0, "gelu": 1, "silu": 2, "gate_res": 3, "qkv_rope": 4, "euler_unpatch": 5, "geglu": 6, "res": 7, "bias_bcast": 8,
 }
 
 
@@ -57,6 +57,30 @@ def gemm(a: torch.Tensor, w: torch.Tensor, mode: str = "bias", **kw) -> None:
     """``out = epilogue(a @ w.T)`` on tcgen05 tensor cores.  ``a``: [M,K] or [B,rows,K] view
     (last dim contiguous), ``w``: [N,K].  See csrc/bind.cpp for the keyword arguments."""
     require().gemm(a, w, EPI[mode], **kw)
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW conv weight -> [Cout_pad32, taps * Cin_pad64] bf16, tap-major (kh, kw), zero padded — the
+    K-major B operand of the implicit-GEMM convolution."""
+    co, ci, kh, kw = w.shape
+    cpad = (ci + 63) // 64 * 64
+    copad = (co + 31) // 32 * 32
+    out = torch.zeros(copad, kh * kw, cpad, dtype=torch.bfloat16, device=w.device)
+    out[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci).to(torch.bfloat16)
+    return out.reshape(copad, kh * kw * cpad).contiguous()
+
+
+def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, taps: int, stride: int = 1, mode: str = "bias",
+                out: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    """3x3 (pad 1) or 1x1 convolution on NHWC bf16 as an implicit GEMM on tcgen05 (TMA does the im2col:
+    shifted 4-D boxes, zero padding from out-of-bounds fill).  Returns [N, Ho*Wo, Cout_pad]."""
+    n, h, wd, _ = x.shape
+    pad, k = (1, 3) if taps == 9 else (0, 1)
+    ho, wo = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
+    if out is None:
+        out = torch.empty(n, ho * wo, w_packed.shape[0], dtype=torch.bfloat16, device=x.device)
+    require().conv(x, w_packed, taps, stride, EPI[mode], out=out, **kw)
+    return out
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: str = "bias",

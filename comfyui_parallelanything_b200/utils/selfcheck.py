@@ -366,3 +366,53 @@ def scatter_patch_embed():
     r["temb_mean_rel"] = r2["mean_rel"]
     r["ok"] = r["ok"] and r2["ok"] and bool(torch.equal(xc, x)) and bool(X[:, :77].abs().max().item() == 0)
     return r
+
+
+# ------------------------------------------------------------------------------ convolution
+def _conv_case(name, N, Cin, H, W, Cout, k, stride, mode="bias"):
+    x = _rand(N, Cin, H, W)
+    w = _rand(Cout, Cin, k, k, scale=(Cin * k * k) ** -0.5)
+    b = _rand(Cout)
+    xh = x.permute(0, 2, 3, 1).contiguous()
+    wp = ops.pack_conv_weight(w)
+    bp = torch.zeros(wp.shape[0], dtype=torch.bfloat16, device=_dev())
+    bp[:Cout] = b
+    kw = {}
+    want = F.conv2d(x.float(), w.float(), b.float(), stride=stride, padding=k // 2)
+    Ho, Wo = want.shape[2], want.shape[3]
+    if mode == "res":
+        res = _rand(N, Ho * Wo, wp.shape[0])
+        kw["residual"] = res
+        want = want + res[..., :Cout].float().view(N, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    if mode == "bias_bcast":
+        emb = _rand(N, wp.shape[0])
+        kw["gate"] = emb
+        want = want + emb[:, :Cout].float()[:, :, None, None]
+    out = ops.conv2d_nhwc(xh, wp, k * k, stride, mode, bias=bp, **kw)
+    got = out[..., :Cout].float().view(N, Ho, Wo, Cout).permute(0, 3, 1, 2)
+    return _cmp(name, got, want, 0.012)
+
+
+@check
+def conv3x3_basic():
+    return _conv_case("conv3x3_basic", 2, 64, 32, 32, 128, 3, 1)
+
+
+@check
+def conv3x3_ragged():
+    r1 = _conv_case("conv3x3_ragged", 1, 320, 24, 40, 320, 3, 1, "bias_bcast")    # Cin = 5x64, W not /16
+    r2 = _conv_case("conv3x3_c8", 2, 8, 16, 16, 32, 3, 1)                          # tiny Cin (padded K)
+    r3 = _conv_case("conv3x3_small_hw", 2, 128, 8, 8, 256, 3, 1, "res")            # 8x8 feature map
+    r1["ok"] = r1["ok"] and r2["ok"] and r3["ok"]
+    r1["c8_mean_rel"], r1["hw8_mean_rel"] = r2["mean_rel"], r3["mean_rel"]
+    return r1
+
+
+@check
+def conv3x3_stride2():
+    return _conv_case("conv3x3_stride2", 2, 128, 32, 48, 128, 3, 2)
+
+
+@check
+def conv1x1():
+    return _conv_case("conv1x1", 2, 192, 16, 24, 320, 1, 1, "res")

@@ -38,25 +38,13 @@ static void view3(const Tensor& t, int& batch, int& rows, long long& ld, long lo
   }
 }
 
-// gemm(A, W, mode, out=..., bias=..., residual=..., gate=..., q=,k=,v=,q_scale=,k_scale=,rope=,heads=,seq_off=,
-//      mlp_col_off=, qk_eps=, x_in=, x_out= | x_out_ptr=, xout_sample_off=, sigmas=, C=,Hl=,Wl=, force_bn=)
-static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
-  TORCH_CHECK(A.is_cuda() && W.is_cuda(), "gemm: CUDA tensors required");
-  TORCH_CHECK(A.scalar_type() == at::kBFloat16 && W.scalar_type() == at::kBFloat16, "gemm: bf16 required");
-  TORCH_CHECK(W.dim() == 2 && W.stride(1) == 1, "gemm: W must be [N, K] with contiguous K");
-  c10::cuda::CUDAGuard guard(A.device());
-  pa::GemmParams p{};
-  long long lda, abs_;
-  view3(A, p.batch, p.rows, lda, abs_);
-  p.N = (int)W.size(0);
-  p.K = (int)W.size(1);
-  TORCH_CHECK(A.size(-1) == p.K, "gemm: K mismatch");
-  p.mode = mode;
+// out= / bias= / residual= / gate= (shared by gemm and conv)
+static void parse_epilogue(const py::kwargs& kw, pa::GemmParams& p, bool check_shape) {
   if (has(kw, "out")) {
     Tensor o = ten(kw, "out");
     int ob, orows;
     view3(o, ob, orows, p.ldc, p.out_bstride);
-    TORCH_CHECK(ob == p.batch && orows == p.rows, "gemm: out shape mismatch");
+    TORCH_CHECK(!check_shape || (ob == p.batch && orows == p.rows), "out shape mismatch");
     p.out = reinterpret_cast<__nv_bfloat16*>(o.data_ptr());
   }
   p.bias = bfp(kw, "bias");
@@ -72,6 +60,23 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
     p.gate = reinterpret_cast<const __nv_bfloat16*>(g.data_ptr());
     p.gate_bstride = g.dim() >= 2 ? g.stride(0) : 0;
   }
+}
+
+// gemm(A, W, mode, out=..., bias=..., residual=..., gate=..., q=,k=,v=,q_scale=,k_scale=,rope=,heads=,seq_off=,
+//      mlp_col_off=, qk_eps=, x_in=, x_out= | x_out_ptr=, xout_sample_off=, sigmas=, C=,Hl=,Wl=, force_bn=)
+static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
+  TORCH_CHECK(A.is_cuda() && W.is_cuda(), "gemm: CUDA tensors required");
+  TORCH_CHECK(A.scalar_type() == at::kBFloat16 && W.scalar_type() == at::kBFloat16, "gemm: bf16 required");
+  TORCH_CHECK(W.dim() == 2 && W.stride(1) == 1, "gemm: W must be [N, K] with contiguous K");
+  c10::cuda::CUDAGuard guard(A.device());
+  pa::GemmParams p{};
+  long long lda, abs_;
+  view3(A, p.batch, p.rows, lda, abs_);
+  p.N = (int)W.size(0);
+  p.K = (int)W.size(1);
+  TORCH_CHECK(A.size(-1) == p.K, "gemm: K mismatch");
+  p.mode = mode;
+  parse_epilogue(kw, p, /*check_shape=*/true);
   if (mode == pa::EPI_QKV_ROPE) {
     Tensor q = ten(kw, "q");
     TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && q.is_contiguous(), "q must be [B, H, L, 128] contiguous");
@@ -116,6 +121,25 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
   }
   int force_bn = has(kw, "force_bn") ? kw["force_bn"].cast<int>() : 0;
   check(pa::gemm_bf16(A.data_ptr(), lda, abs_, W.data_ptr(), W.stride(0), p, force_bn, cur_stream()), "gemm_bf16");
+}
+
+// conv(x[N,H,W,Cin], w[Cout, taps*Cin_pad], taps, stride, mode, out=[N, Ho*Wo, Cout], bias=, residual=, gate=)
+static void conv(Tensor x, Tensor w, int taps, int stride, int mode, py::kwargs kw) {
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous() && x.scalar_type() == at::kBFloat16,
+              "conv: x must be a contiguous NHWC bf16 tensor [N, H, W, C]");
+  TORCH_CHECK(w.dim() == 2 && w.is_contiguous() && w.scalar_type() == at::kBFloat16, "conv: w must be [Cout, taps*Cin_pad]");
+  c10::cuda::CUDAGuard guard(x.device());
+  pa::GemmParams p{};
+  p.mode = mode;
+  p.N = (int)w.size(0);
+  const int Cin = (int)x.size(3);
+  const int cpad = (Cin + 63) / 64 * 64;
+  TORCH_CHECK(w.size(1) == (int64_t)taps * cpad, "conv: weight K must be taps * 64*ceil(Cin/64)");
+  parse_epilogue(kw, p, /*check_shape=*/false);
+  TORCH_CHECK(p.out != nullptr, "conv: out= required");
+  check(pa::conv_bf16(x.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), Cin, w.data_ptr(), taps, stride, p,
+                      cur_stream()),
+        "conv_bf16");
 }
 
 static void layernorm_modulate(Tensor x, Tensor out, c10::optional<Tensor> scale, c10::optional<Tensor> shift,
@@ -239,6 +263,7 @@ static void wait_flags(Tensor flags, int first, int n, uint32_t value, long long
 PYBIND11_MODULE(_C, m) {
   m.doc() = "comfyui-parallelanything_b200 native library (sm_100a kernels + runtime)";
   m.def("gemm", &gemm, py::arg("A"), py::arg("W"), py::arg("mode"));
+  m.def("conv", &conv, py::arg("x"), py::arg("w"), py::arg("taps"), py::arg("stride"), py::arg("mode"));
   m.def("layernorm_modulate", &layernorm_modulate, py::arg("x"), py::arg("out"), py::arg("scale") = py::none(),
         py::arg("shift") = py::none(), py::arg("gamma") = py::none(), py::arg("beta") = py::none(),
         py::arg("eps") = 1e-6);
@@ -262,4 +287,5 @@ PYBIND11_MODULE(_C, m) {
   m.attr("EPI_EULER_UNPATCH") = (int)pa::EPI_EULER_UNPATCH;
   m.attr("EPI_GEGLU") = (int)pa::EPI_GEGLU;
   m.attr("EPI_RES") = (int)pa::EPI_RES;
+  m.attr("EPI_BIAS_BCAST") = (int)pa::EPI_BIAS_BCAST;
 }

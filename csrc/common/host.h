@@ -13,7 +13,9 @@ int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& 
 
 int num_sms();
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes);
+              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides = nullptr);
+int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int taps, int stride, GemmParams p,
+              cudaStream_t st);
 
 int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, GemmParams p,
               int force_bn, cudaStream_t st);

@@ -26,8 +26,8 @@ constexpr uint32_t SLICE_BYTES = 128 * 64 * 2;
 constexpr uint32_t OFF_Q = 0;
 constexpr uint32_t OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
 constexpr uint32_t OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
-constexpr uint32_t OFF_P = OFF_V + 2 * TILE_BYTES;
-constexpr uint32_t OFF_BAR = OFF_P + TILE_BYTES;
+constexpr uint32_t OFF_P = OFF_V + 2 * TILE_BYTES;  // 2 buffers
+constexpr uint32_t OFF_BAR = OFF_P + 2 * TILE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 512;                 // S0 S1 O0 O1, 128 fp32 columns each
 }  // namespace attn
@@ -62,6 +62,35 @@ __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigne
   return d;
 }
 
+// 2^x for two packed floats without the SFU: n = round(x) via the 1.5*2^23 magic constant, 2^f on
+// [-0.5, 0.5] by a degree-4 polynomial (rel. error ~4e-5, far below bf16 resolution), exponent patched in
+// with integer adds.  x must be <= ~100; very negative inputs are clamped (result underflows to ~2^-126).
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const unsigned long long x = pack2(x0, x1);
+  const unsigned long long magic = pack2(12582912.0f, 12582912.0f);
+  const unsigned long long nmagic = pack2(-12582912.0f, -12582912.0f);
+  const unsigned long long xr = add2(x, magic);                    // low mantissa bits = round(x)
+  const unsigned long long nf = add2(xr, nmagic);                  // round(x) as float
+  float n0, n1, f0, f1;
+  unpack2(nf, n0, n1);
+  const unsigned long long f = add2(x, pack2(-n0, -n1));
+  unsigned long long p = pack2(0.009618129f, 0.009618129f);
+  p = fma2(p, f, pack2(0.05550411f, 0.05550411f));
+  p = fma2(p, f, pack2(0.2402265f, 0.2402265f));
+  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, xr0, xr1;
+  unpack2(p, p0, p1);
+  unpack2(xr, xr0, xr1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xr0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xr1) << 23));
+  (void)f0; (void)f1;
+}
+
 __global__ void __launch_bounds__(256, 1)
 attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
@@ -79,9 +108,9 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* s_empty = bars + 11;      // 2
   uint64_t* o_full = bars + 13;       // 2
   uint64_t* o_empty = bars + 15;      // 2
-  uint64_t* p_full = bars + 17;       // 1
-  uint64_t* p_empty = bars + 18;      // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* p_full = bars + 17;       // 2
+  uint64_t* p_empty = bars + 19;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM;
@@ -105,8 +134,10 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&o_empty[i], 4);      // (unused since O accumulates in TMEM)
     }
-    ptx::mbar_init(p_full, 4);
-    ptx::mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_empty[i], 1);
+    }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
   }
@@ -162,18 +193,19 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (j + 1 < n_kv) issue_qk(j + 1);
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(&p_full[s], ph);
         ptx::mbar_wait(&v_full[s], ph);
         ptx::tc_fence_after();
         const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + s * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t a = ptx::make_desc_kmajor_sw128(p_addr + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
+          const uint64_t a =
+              ptx::make_desc_kmajor_sw128(p_addr + s * TILE_BYTES + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
           const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
           ptx::mma_f16_ss(tmem + 256, a, b, IDESC_PV, (j | kk) != 0);
         }
         ptx::tc_commit(&v_empty[s]);
-        ptx::tc_commit(p_empty);
+        ptx::tc_commit(&p_empty[s]);
         ptx::tc_commit(&o_full[0]);          // phase j & 1: "O includes tiles 0..j"
       }
     }
@@ -183,7 +215,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     const uint32_t o_addr = lane_addr + 256;
     float m_used = -INFINITY, l = 0.f;
-    uint8_t* p_row = smem + OFF_P + r * 128;
+    uint8_t* p_row0 = smem + OFF_P + r * 128;
     const int sw = r & 7;
     const unsigned long long sl2 = pack2(scale_log2, scale_log2);
 
@@ -246,7 +278,8 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
-      ptx::mbar_wait(p_empty, (j & 1) ^ 1);             // PV of tile j-1 has consumed the P buffer
+      ptx::mbar_wait(&p_empty[s], ((j >> 1) & 1) ^ 1);  // PV of tile j-2 has consumed this P buffer
+      uint8_t* p_row = p_row0 + s * TILE_BYTES;
       unsigned long long sum2 = pack2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -254,9 +287,17 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a0, a1;
-          unpack2(fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg), a0, a1);
-          a0 = ex2f(a0);
-          a1 = ex2f(a1);
+          const unsigned long long x2 =
+              fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg);
+          if ((i >> 1) & 1) {
+            // MUFU.EX2 is only 16 lanes/clk/SM on sm_100 (as slow as the two MMAs of this tile): every
+            // second pair goes through a Cody-Waite + degree-4 polynomial on the FMA pipe instead.
+            exp2_poly2(x2, a0, a1);
+          } else {
+            unpack2(x2, a0, a1);
+            a0 = ex2f(a0);
+            a1 = ex2f(a1);
+          }
           sum2 = add2(sum2, pack2(a0, a1));
           __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
@@ -274,7 +315,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       l += s0 + s1;
       ptx::fence_proxy_async_smem();     // P_j (generic-proxy stores) visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
+      if (lane == 0) ptx::mbar_arrive(&p_full[s]);
     }
 
     // ---- epilogue: O / l -> bf16
@@ -323,13 +364,13 @@ int attention_d128(const void* q, const void* k, const void* v, void* out, long 
   {
     uint64_t dims[3] = {128, (uint64_t)Lq, (uint64_t)B * H};
     uint64_t str[3] = {2, 256, (uint64_t)Lq * 256};
-    if (make_tmap(&tq, q, 3, dims, str, box, 2)) return -20;
+    if (make_tmap(&tq, q, 3, dims, str, box, 2, nullptr)) return -20;
   }
   {
     uint64_t dims[3] = {128, (uint64_t)Lk, (uint64_t)B * H};
     uint64_t str[3] = {2, 256, (uint64_t)Lk * 256};
-    if (make_tmap(&tk, k, 3, dims, str, box, 2)) return -21;
-    if (make_tmap(&tv, v, 3, dims, str, box, 2)) return -22;
+    if (make_tmap(&tk, k, 3, dims, str, box, 2, nullptr)) return -21;
+    if (make_tmap(&tv, v, 3, dims, str, box, 2, nullptr)) return -22;
   }
   static bool attr_set[64] = {false};
   int dev = 0;

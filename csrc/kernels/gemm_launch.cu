@@ -25,7 +25,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // rank-N bf16/u8 tensor map with 128-byte swizzle.  dims/strides innermost first; strides[0] is implicit.
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes) {
+              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides) {
   auto fn = encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[5], gstr[4];
@@ -33,7 +33,7 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
@@ -95,17 +95,71 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
   }
   if (p.mode == EPI_QKV_ROPE && bn < 128) return -12;
   CUtensorMap ta, tb;
+  if (p.conv_taps > 0) return -30;   // use conv_bf16()
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
     uint64_t str[3] = {2, (uint64_t)lda * 2, (uint64_t)(p.batch > 1 ? a_bstride : (long long)p.rows * lda) * 2};
     uint32_t box[3] = {64, 128, 1};
-    if (make_tmap(&ta, A, 3, dims, str, box, 2)) return -20;
+    if (make_tmap(&ta, A, 3, dims, str, box, 2, nullptr)) return -20;
   }
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t str[2] = {2, (uint64_t)ldw * 2};
     uint32_t box[2] = {64, (uint32_t)bn};
-    if (make_tmap(&tb, W, 2, dims, str, box, 2)) return -21;
+    if (make_tmap(&tb, W, 2, dims, str, box, 2, nullptr)) return -21;
+  }
+  const int tiles = m_tiles * ((p.N + bn - 1) / bn);
+  switch (bn) {
+    case 256: return launch<256>(ta, tb, p, tiles, st);
+    case 128: return launch<128>(ta, tb, p, tiles, st);
+    case 64: return launch<64>(ta, tb, p, tiles, st);
+  }
+  return -13;
+}
+
+// Implicit-GEMM convolution on NHWC bf16:  x [N, H, W, Cin] (Cin % 8 == 0), w [Cout, taps, Cin_pad] with
+// Cin_pad = 64 * ceil(Cin / 64) (zero padded), out [N, Ho*Wo, Cout] through the usual epilogues.
+int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int taps, int stride, GemmParams p,
+              cudaStream_t st) {
+  if (Cin % 8 || p.N % 32 || (taps != 1 && taps != 9)) return -10;
+  const int pad = taps == 9 ? 1 : 0;
+  const int Ho = (H + 2 * pad - (taps == 9 ? 3 : 1)) / stride + 1;
+  const int Wo = (W + 2 * pad - (taps == 9 ? 3 : 1)) / stride + 1;
+  const int tw = Wo >= 16 ? 16 : (Wo >= 8 ? 8 : 4);
+  const int th = 128 / tw;
+  p.conv_taps = taps;
+  p.conv_cblocks = (Cin + 63) / 64;
+  p.conv_tw = tw; p.conv_th = th; p.conv_wo = Wo; p.conv_ho = Ho;
+  p.conv_stride = stride; p.conv_pad = pad;
+  p.conv_tiles_w = (Wo + tw - 1) / tw;
+  p.conv_tiles_h = (Ho + th - 1) / th;
+  p.rows = Ho * Wo;
+  p.batch = N;
+  p.K = taps * p.conv_cblocks * 64;
+  const int m_tiles = p.conv_tiles_w * p.conv_tiles_h * N;
+  int bn = 64;
+  const int cands[3] = {256, 128, 64};
+  for (int c : cands) {
+    if (p.N % c && p.N > c) continue;
+    if (m_tiles * ((p.N + c - 1) / c) >= num_sms() || c == 64) { bn = c; break; }
+  }
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[4] = {2, (uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)(tw * stride), (uint32_t)(th * stride), 1};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (stride > 1) {            // the box spans (t-1)*stride + 1 input elements
+      box[1] = (uint32_t)((tw - 1) * stride + 1);
+      box[2] = (uint32_t)((th - 1) * stride + 1);
+    }
+    if (make_tmap(&ta, x, 4, dims, str, box, 2, es)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {2, (uint64_t)p.K * 2};
+    uint32_t box[2] = {64, (uint32_t)bn};
+    if (make_tmap(&tb, w, 2, dims, str, box, 2, nullptr)) return -21;
   }
   const int tiles = m_tiles * ((p.N + bn - 1) / bn);
   switch (bn) {

@@ -14,6 +14,7 @@ enum EpiMode : int {
   EPI_EULER_UNPATCH = 5,// N = C*ps*ps : velocity -> x_next written in NCHW, possibly to a peer
   EPI_GEGLU = 6,        // W rows interleaved [a(32) | g(32)]...: out[:, n/2] = a * gelu(g)
   EPI_RES = 7,          // out = residual + acc + bias
+  EPI_BIAS_BCAST = 8,   // out = acc + bias + gate[b, n]   (per-sample channel bias, e.g. time embedding)
 };
 
 struct GemmParams {
@@ -43,6 +44,15 @@ struct GemmParams {
   long long xout_sample_off;        // first sample of this rank inside x_out
   const float* sigmas;              // [batch, 2] (sigma, sigma_next) per sample, or nullptr => out = v
   int C, Hl, Wl, ps;
+  // implicit-GEMM convolution: A is an NHWC activation addressed through a 4-D TMA tensor
+  // (C, W, H, N); the K loop walks taps x Cin-blocks with shifted spatial coordinates, padding
+  // comes from TMA out-of-bounds zero fill.  rows = Ho*Wo, batch = N.
+  int conv_taps;             // 0 = plain GEMM, 1 (1x1) or 9 (3x3)
+  int conv_cblocks;          // ceil(Cin / 64)
+  int conv_tw, conv_th;      // spatial tile, tw * th == 128
+  int conv_wo, conv_ho;      // output size
+  int conv_stride, conv_pad;
+  int conv_tiles_w, conv_tiles_h;
 };
 
 }  // namespace pa

@@ -128,11 +128,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_per_batch = (p.rows + BM - 1) / BM;
+  const bool conv = p.conv_taps > 0;
+  const int m_per_batch = conv ? p.conv_tiles_w * p.conv_tiles_h : (p.rows + BM - 1) / BM;
   const int num_m = m_per_batch * p.batch;
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
-  const int num_k = (p.K + BK - 1) / BK;
+  const int num_k = conv ? p.conv_taps * p.conv_cblocks : (p.K + BK - 1) / BK;
   constexpr int GROUP_M = 8;
 
   auto decode = [&](int t, int& mt, int& nt) {
@@ -154,11 +155,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         int mt, nt;
         decode(t, mt, nt);
         const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
+        int h0 = 0, w0 = 0;
+        if (conv) {
+          const int t_in = mt - b * m_per_batch;
+          const int ti_h = t_in / p.conv_tiles_w;
+          h0 = ti_h * p.conv_th * p.conv_stride - p.conv_pad;
+          w0 = (t_in - ti_h * p.conv_tiles_w) * p.conv_tw * p.conv_stride - p.conv_pad;
+        }
         for (int kb = 0; kb < num_k; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          ptx::tma_load_3d(sa, &tmA, &full[stage], kb * BK, mrow, b);
+          if (conv) {
+            const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
+            const int kh = p.conv_taps == 9 ? tap / 3 : 0, kw = p.conv_taps == 9 ? tap - kh * 3 : 0;
+            ptx::tma_load_4d(sa, &tmA, &full[stage], cb * BK, w0 + kw, h0 + kh, b);
+          } else {
+            ptx::tma_load_3d(sa, &tmA, &full[stage], kb * BK, mrow, b);
+          }
           ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -202,8 +216,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int mt, nt;
       decode(t, mt, nt);
       const int b = mt / m_per_batch;
-      const int row = (mt - b * m_per_batch) * BM + r_in_tile;
-      const bool row_ok = row < p.rows;
+      int row = (mt - b * m_per_batch) * BM + r_in_tile;
+      bool row_ok = row < p.rows;
+      if (conv) {
+        const int t_in = mt - b * m_per_batch;
+        const int ti_h = t_in / p.conv_tiles_w;
+        const int rh = r_in_tile / p.conv_tw;
+        const int oh = ti_h * p.conv_th + rh;
+        const int ow = (t_in - ti_h * p.conv_tiles_w) * p.conv_tw + (r_in_tile - rh * p.conv_tw);
+        row_ok = oh < p.conv_ho && ow < p.conv_wo;
+        row = oh * p.conv_wo + ow;
+      }
       const int n0 = nt * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -372,6 +395,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             } else if (p.mode == EPI_BIAS_SILU) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = silu(x[e]);
+            } else if (p.mode == EPI_BIAS_BCAST) {
+              float gv[8];
+              ldg8(grow + n + g * 8, gv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] += gv[e];
             } else if ((p.mode == EPI_GATE_RES || p.mode == EPI_RES) && row_ok) {
               float res[8];
               ld8(rrow + n + g * 8, res);
