@@ -271,6 +271,10 @@ def run_reference(args) -> int:
         params, host = synthetic_inputs(B, pinned=True)
         torch.manual_seed(1234)
         lead = torch.device("cuda", 0)
+        # The reference rebuilds replicas with ``model_class(**config)`` (ADP:622) and copies weights INTO
+        # them (ADP:656), so a replica gets the process' default dtype: run this arm with bf16 as the
+        # default dtype (as a bf16 ComfyUI model would construct itself), otherwise clones would be fp32.
+        torch.set_default_dtype(torch.bfloat16)
         with torch.device(lead):
             model = flux.Flux(params, dtype=torch.bfloat16).eval()
         chain = None
@@ -278,6 +282,10 @@ def run_reference(args) -> int:
         for i in range(args.gpus):
             chain = ref.ParallelDevice().add_device(f"cuda:{i}", pct, chain)[0]
         (model,) = ref.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
+        # The reference clones through ``source_model.cpu()`` in place (ADP:600-605) and leaves the original
+        # stranded on the host; in ComfyUI ``load_models_gpu`` puts the MODEL back on ``load_device`` before
+        # sampling.  The harness plays that role (nn.Module.to is a no-op for the N=1 case).
+        torch.nn.Module.to(model, lead)
         d = {k: v.to(lead) for k, v in host.items()}
         stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
         result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()

@@ -416,3 +416,22 @@ def conv3x3_stride2():
 @check
 def conv1x1():
     return _conv_case("conv1x1", 2, 192, 16, 24, 320, 1, 1, "res")
+
+
+@check
+def attention_d64_strided():
+    """head_dim 64 (SDXL) straight from a fused [B, L, 3*H*D] QKV GEMM output (strided 4-D TMA views),
+    plus a short cross-attention (Lk = 77)."""
+    B, H, L, D = 2, 10, 1024, 64
+    qkv = _rand(B, L, 3, H, D)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))       # [B, H, L, D] views, no copies
+    out = ops.attention(q, k, v)
+    want = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, L, H * D)
+    r = _cmp("attention_d64_strided", out, want, 0.02)
+    kc, vc = _rand(B, 77, H, D, seed=5).permute(0, 2, 1, 3), _rand(B, 77, H, D, seed=6).permute(0, 2, 1, 3)
+    out2 = ops.attention(q, kc, vc)
+    want2 = F.scaled_dot_product_attention(q.float(), kc.float(), vc.float()).transpose(1, 2).reshape(B, L, H * D)
+    r2 = _cmp("cross77", out2, want2, 0.02)
+    r["cross77_mean_rel"] = r2["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r

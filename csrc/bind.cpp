@@ -217,11 +217,19 @@ static void add_(Tensor a, Tensor b, Tensor out) {
 
 static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale) {
   c10::cuda::CUDAGuard guard(q.device());
-  TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && q.is_contiguous() && k.is_contiguous() && v.is_contiguous());
-  TORCH_CHECK(out.dim() == 3 && out.stride(2) == 1, "out must be [B, L, H*128] (row stride free)");
-  check(pa::attention_d128(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
-                           (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), (float)scale, cur_stream()),
-        "attention_d128");
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "q/k/v must be [B, H, L, D] views");
+  const int D = (int)q.size(3);
+  TORCH_CHECK((D == 64 || D == 128) && k.size(3) == D && v.size(3) == D, "head_dim must be 64 or 128");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1, "innermost dim must be contiguous");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16, "bf16 required");
+  TORCH_CHECK(out.dim() == 3 && out.stride(2) == 1, "out must be [B, L, H*D] (row stride free)");
+  long long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
+  long long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
+  long long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  check(pa::attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
+                           (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale,
+                           cur_stream()),
+        "attention");
 }
 
 static void groupnorm_silu(Tensor x, Tensor out, Tensor gamma, Tensor beta, int groups, double eps, bool silu) {

@@ -37,9 +37,10 @@ int patchify(const void* x, void* out, long long ldo, long long o_bstride, int B
 int silu_bf16(const void* x, void* out, long long n, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st);
 
-// fused attention (head_dim 128, bf16): q,k,v [BH, L, 128] -> out[b, l, h*128 + d] with row stride ldo
-int attention_d128(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride,
-                   int B, int H, int Lq, int Lk, float scale, cudaStream_t st);
+// fused attention (head_dim 64 / 128, bf16): q,k,v [B, H, L, D] strided views -> out[b, l, h*D + d]
+int attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                   int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
+                   const long long* v_strides, float scale, cudaStream_t st);
 
 // GroupNorm (+ optional SiLU) on NHWC bf16
 int groupnorm_silu_nhwc_ws(const void* x, void* out, const void* gamma, const void* beta, float* workspace, int B,

@@ -19,18 +19,20 @@
 
 namespace pa {
 
-namespace attn {
-constexpr int BM = 128, BN = 128, D = 128;
-constexpr uint32_t TILE_BYTES = 128 * 128 * 2;     // 32 KB: two 16 KB slices of [128 rows][64 elems]
-constexpr uint32_t SLICE_BYTES = 128 * 64 * 2;
-constexpr uint32_t OFF_Q = 0;
-constexpr uint32_t OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
-constexpr uint32_t OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
-constexpr uint32_t OFF_P = OFF_V + 2 * TILE_BYTES;  // 2 buffers
-constexpr uint32_t OFF_BAR = OFF_P + 2 * TILE_BYTES;
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr uint32_t TMEM_COLS = 512;                 // S0 S1 O0 O1, 128 fp32 columns each
-}  // namespace attn
+template <int D>
+struct AttnCfg {
+  static constexpr int BM = 128, BN = 128;
+  static constexpr uint32_t SLICE_BYTES = 128 * 64 * 2;            // [128 rows][64 elems], 128B-swizzled
+  static constexpr uint32_t QKV_TILE = 128 * D * 2;                // D/64 slices
+  static constexpr uint32_t P_TILE = 128 * 128 * 2;
+  static constexpr uint32_t OFF_Q = 0;
+  static constexpr uint32_t OFF_K = OFF_Q + QKV_TILE;              // 2 stages
+  static constexpr uint32_t OFF_V = OFF_K + 2 * QKV_TILE;          // 2 stages
+  static constexpr uint32_t OFF_P = OFF_V + 2 * QKV_TILE;          // 2 buffers
+  static constexpr uint32_t OFF_BAR = OFF_P + 2 * P_TILE;
+  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;                       // S0 @0, S1 @128, O @256 (D columns)
+};
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -91,11 +93,16 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, flo
   (void)f0; (void)f1;
 }
 
+template <int D>
 __global__ void __launch_bounds__(256, 1)
-attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                      const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
-                      long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
-  using namespace attn;
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
+                 long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
+  using Cfg = AttnCfg<D>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN;
+  constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES, TILE_BYTES = Cfg::QKV_TILE, P_TILE = Cfg::P_TILE;
+  constexpr uint32_t OFF_Q = Cfg::OFF_Q, OFF_K = Cfg::OFF_K, OFF_V = Cfg::OFF_V, OFF_P = Cfg::OFF_P,
+                     OFF_BAR = Cfg::OFF_BAR, TMEM_COLS = Cfg::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -149,26 +156,30 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      const int hb = bh / H, hh = bh - hb * H;
       ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      ptx::tma_load_3d(smem + OFF_Q, &tmQ, q_full, 0, q0, bh);
-      ptx::tma_load_3d(smem + OFF_Q + SLICE_BYTES, &tmQ, q_full, 64, q0, bh);
+#pragma unroll
+      for (int sl = 0; sl < D / 64; ++sl)
+        ptx::tma_load_4d(smem + OFF_Q + sl * SLICE_BYTES, &tmQ, q_full, sl * 64, q0, hh, hb);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
-        ptx::tma_load_3d(smem + OFF_K + s * TILE_BYTES, &tmK, &k_full[s], 0, j * BN, bh);
-        ptx::tma_load_3d(smem + OFF_K + s * TILE_BYTES + SLICE_BYTES, &tmK, &k_full[s], 64, j * BN, bh);
+#pragma unroll
+        for (int sl = 0; sl < D / 64; ++sl)
+          ptx::tma_load_4d(smem + OFF_K + s * TILE_BYTES + sl * SLICE_BYTES, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
         ptx::mbar_wait(&v_empty[s], ph ^ 1);
         ptx::mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
-        ptx::tma_load_3d(smem + OFF_V + s * TILE_BYTES, &tmV, &v_full[s], 0, j * BN, bh);
-        ptx::tma_load_3d(smem + OFF_V + s * TILE_BYTES + SLICE_BYTES, &tmV, &v_full[s], 64, j * BN, bh);
+#pragma unroll
+        for (int sl = 0; sl < D / 64; ++sl)
+          ptx::tma_load_4d(smem + OFF_V + s * TILE_BYTES + sl * SLICE_BYTES, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
-      constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, 128, 1, 0, 1);   // B (= V) is MN-major
+      constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);     // B (= V) is MN-major, N = D
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
       const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
       auto issue_qk = [&](int i) {
@@ -179,7 +190,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::tc_fence_after();
         const uint32_t k_addr = ptx::smem_u32(smem + OFF_K + s * TILE_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
+        for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t off = (kk >> 2) * SLICE_BYTES + (kk & 3) * 32;
           ptx::mma_f16_ss(tmem + s * 128, ptx::make_desc_kmajor_sw128(q_addr + off),
                           ptx::make_desc_kmajor_sw128(k_addr + off), IDESC_QK, kk != 0);
@@ -200,7 +211,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t a =
-              ptx::make_desc_kmajor_sw128(p_addr + s * TILE_BYTES + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
+              ptx::make_desc_kmajor_sw128(p_addr + s * P_TILE + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
           const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
           ptx::mma_f16_ss(tmem + 256, a, b, IDESC_PV, (j | kk) != 0);
         }
@@ -264,7 +275,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           ptx::mbar_wait(&o_full[0], (j - 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < D / 32; ++c) {
             uint32_t t[32];
             ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
             ptx::tmem_ld_wait();
@@ -279,7 +290,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
       ptx::mbar_wait(&p_empty[s], ((j >> 1) & 1) ^ 1);  // PV of tile j-2 has consumed this P buffer
-      uint8_t* p_row = p_row0 + s * TILE_BYTES;
+      uint8_t* p_row = p_row0 + s * P_TILE;
       unsigned long long sum2 = pack2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -326,7 +337,7 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int b = bh / H, h = bh - b * H;
     __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < D / 32; ++c) {
       uint32_t t[32];
       ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
       ptx::tmem_ld_wait();
@@ -352,40 +363,53 @@ attention_d128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<attn::TMEM_COLS>(tmem);
+    ptx::tmem_dealloc<TMEM_COLS>(tmem);
   }
 }
 
-int attention_d128(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
-                   int H, int Lq, int Lk, float scale, cudaStream_t st) {
-  using namespace attn;
+template <int D>
+static int launch_attention(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride,
+                            int B, int H, int Lq, int Lk, const long long* qs, const long long* ks,
+                            const long long* vs, float scale, cudaStream_t st) {
+  using Cfg = AttnCfg<D>;
   CUtensorMap tq, tk, tv;
-  const uint32_t box[3] = {64, 128, 1};
-  {
-    uint64_t dims[3] = {128, (uint64_t)Lq, (uint64_t)B * H};
-    uint64_t str[3] = {2, 256, (uint64_t)Lq * 256};
-    if (make_tmap(&tq, q, 3, dims, str, box, 2, nullptr)) return -20;
-  }
-  {
-    uint64_t dims[3] = {128, (uint64_t)Lk, (uint64_t)B * H};
-    uint64_t str[3] = {2, 256, (uint64_t)Lk * 256};
-    if (make_tmap(&tk, k, 3, dims, str, box, 2, nullptr)) return -21;
-    if (make_tmap(&tv, v, 3, dims, str, box, 2, nullptr)) return -22;
-  }
+  const uint32_t box[4] = {64, 128, 1, 1};
+  auto mk = [&](CUtensorMap* m, const void* p, int L, const long long* s3) {   // s3 = (b, h, l) strides in elements
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {2, (uint64_t)s3[2] * 2, (uint64_t)s3[1] * 2, (uint64_t)s3[0] * 2};
+    return make_tmap(m, p, 4, dims, str, box, 2, nullptr);
+  };
+  if (mk(&tq, q, Lq, qs)) return -20;
+  if (mk(&tk, k, Lk, ks)) return -21;
+  if (mk(&tv, v, Lk, vs)) return -22;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_d128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
-  dim3 grid((Lq + BM - 1) / BM, B * H);
+  dim3 grid((Lq + Cfg::BM - 1) / Cfg::BM, B * H);
   const float scale_log2 = scale * 1.4426950408889634f;
-  attention_d128_kernel<<<grid, 256, SMEM_BYTES, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H,
-                                                       Lq, Lk, scale_log2);
+  attention_kernel<D><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride,
+                                                         H, Lq, Lk, scale_log2);
   return (int)cudaGetLastError();
+}
+
+// q/k/v are [B, H, L, D] views given by (batch, head, row) strides in elements (innermost stride 1):
+// both the head-split layout written by the fused QKV epilogue and plain [B, L, H*D] GEMM outputs work.
+int attention_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                   int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
+                   const long long* v_strides, float scale, cudaStream_t st) {
+  for (int i = 0; i < 3; ++i)
+    if (q_strides[i] % 8 || k_strides[i] % 8 || v_strides[i] % 8) return -10;
+  if (D == 128)
+    return launch_attention<128>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, q_strides, k_strides, v_strides, scale, st);
+  if (D == 64)
+    return launch_attention<64>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, q_strides, k_strides, v_strides, scale, st);
+  return -11;
 }
 
 }  // namespace pa
