@@ -283,9 +283,15 @@ def run_reference(args) -> int:
             chain = ref.ParallelDevice().add_device(f"cuda:{i}", pct, chain)[0]
         (model,) = ref.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
         # The reference clones through ``source_model.cpu()`` in place (ADP:600-605) and leaves the original
-        # stranded on the host; in ComfyUI ``load_models_gpu`` puts the MODEL back on ``load_device`` before
-        # sampling.  The harness plays that role (nn.Module.to is a no-op for the N=1 case).
-        torch.nn.Module.to(model, lead)
+        # (= the replica it re-uses for the lead device) stranded on the host; in ComfyUI the model manager
+        # puts the MODEL back on ``load_device`` before sampling and the reference repairs it itself on the
+        # next setup (ADP:932-961).  The harness plays that role: only tensors that are on the CPU are moved
+        # (a blanket ``model.to(lead)`` would also drag the other replicas' blocks along, because the
+        # reference registers them as submodules of the lead model through ``ParallelBlock``).
+        with torch.no_grad():
+            for t_ in list(model.parameters()) + list(model.buffers()):
+                if t_.device.type == "cpu":
+                    t_.data = t_.data.to(lead)
         d = {k: v.to(lead) for k, v in host.items()}
         stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
         result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()

@@ -19,4 +19,8 @@ def builder_for(module: nn.Module) -> Optional[Callable]:
                 and module.params.patch_size == 2:
             from .flux_exec import build_flux_executor
             return build_flux_executor
+    if fam == "unet":
+        from . import unet_exec
+        if unet_exec.supports(module):
+            return unet_exec.build_unet_executor
     return None

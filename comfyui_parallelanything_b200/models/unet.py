@@ -272,6 +272,13 @@ def tiny_config(adm: Optional[int] = None) -> dict:
                 adm_in_channels=adm, use_linear_in_transformer=adm is not None)
 
 
+def mini_sdxl_config() -> dict:
+    """SDXL-shaped (head_dim 64, linear transformer projections, adm conditioning) but small."""
+    return dict(in_channels=4, model_channels=64, out_channels=4, num_res_blocks=1, channel_mult=[1, 2, 2],
+                transformer_depth=[0, 1, 2], context_dim=128, num_heads=-1, num_head_channels=64,
+                adm_in_channels=64, use_linear_in_transformer=True, transformer_depth_middle=2)
+
+
 def example_inputs(cfg: dict, batch: int, height: int, width: int, ctx_len: int = 77, device="cpu",
                    dtype=torch.float32, seed: int = 0):
     g = torch.Generator(device="cpu").manual_seed(seed)

@@ -435,3 +435,66 @@ def attention_d64_strided():
     r["cross77_mean_rel"] = r2["mean_rel"]
     r["ok"] = r["ok"] and r2["ok"]
     return r
+
+
+@check
+def layout_kernels():
+    C_ = ops.require()
+    x = _rand(2, 4, 12, 20)
+    nh = torch.zeros(2, 12 * 20, 8, dtype=torch.bfloat16, device=_dev())
+    C_.nchw_to_nhwc_pad(x.data_ptr(), nh, 2, 4, 240)
+    ok = torch.equal(nh[..., :4], x.permute(0, 2, 3, 1).reshape(2, 240, 4)) and nh[..., 4:].abs().max().item() == 0
+    a = _rand(2, 6, 10, 32)
+    up = torch.empty(2, 12, 20, 32, dtype=torch.bfloat16, device=_dev())
+    C_.upsample2x(a, up)
+    ok = ok and torch.equal(up, F.interpolate(a.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+                            .permute(0, 2, 3, 1).to(torch.bfloat16))
+    b = _rand(2, 60, 64, seed=3)
+    cat = torch.empty(2, 60, 96, dtype=torch.bfloat16, device=_dev())
+    C_.concat_channels(a.view(2, 60, 32), b, cat)
+    ok = ok and torch.equal(cat, torch.cat([a.view(2, 60, 32), b], -1))
+    # gather with CFG pairs + Euler
+    eps = _rand(4, 240, 32)
+    xs = _rand(2, 4, 12, 20, seed=7)
+    sig = torch.tensor([[1.0, 0.7], [0.5, 0.4]], device=_dev())
+    out = torch.zeros(3, 4, 12, 20, dtype=torch.bfloat16, device=_dev())
+    C_.unet_out_gather(eps, xs, out.data_ptr(), sig, 2, 4, True, 5.0, 1, 1)
+    e = eps[..., :4].float().view(4, 12, 20, 4).permute(0, 3, 1, 2)
+    dref = e[2:] + 5.0 * (e[:2] - e[2:])
+    want = xs.float() + (sig[:, 1] - sig[:, 0])[:, None, None, None] * dref
+    r = _cmp("layout_kernels", out[1:], want, 0.012)
+    r["ok"] = r["ok"] and bool(ok) and bool(out[0].abs().max().item() == 0)
+    return r
+
+
+@check
+def unet_executor_mini():
+    from ..exec.unet_exec import UNetExecutor
+    from ..models import unet
+    cfg = unet.mini_sdxl_config()
+    torch.manual_seed(3)
+    m = unet.UNetModel(**cfg).to(device=_dev(), dtype=torch.bfloat16).eval()
+    ex = UNetExecutor(m, _dev())
+    oracle = unet.UNetModel(**cfg).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    inp = unet.example_inputs(cfg, 2, 256, 384, ctx_len=77, device=_dev(), dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = ex(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+        eager = m(**inp)
+    r = _cmp("unet_executor_mini", got, want, 0.03)
+    r["eager_bf16_mean_rel"] = _cmp("eager", eager, want, 1.0)["mean_rel"]
+    # fused gather: CFG pairs + Euler
+    sig = torch.tensor([[14.6, 10.0]], device=_dev())
+    x2 = torch.cat([inp["x"][:1], inp["x"][:1]])
+    t2 = torch.cat([inp["timesteps"][:1]] * 2)
+    c2, y2 = inp["context"], inp["y"]
+    nxt = ex.denoise_step(x2, t2, c2, y2, sig, cfg_scale=4.0, cfg_pairs=True)
+    with torch.no_grad():
+        e2 = oracle(x2.float(), t2.float(), context=c2.float(), y=y2.float())
+    d = e2[1:] + 4.0 * (e2[:1] - e2[1:])
+    want2 = x2[:1].float() + (sig[:, 1] - sig[:, 0]) * d
+    r2 = _cmp("unet_euler", nxt, want2, 0.04)
+    r["euler_mean_rel"] = r2["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r

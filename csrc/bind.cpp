@@ -203,6 +203,59 @@ static void scatter_patch_embed(Tensor W, Tensor bias, uintptr_t x_src, uintptr_
   check(pa::scatter_patch_embed(W.data_ptr(), W.stride(0), p, cur_stream()), "scatter_patch_embed");
 }
 
+static void nchw_to_nhwc_pad(uintptr_t x_ptr, Tensor out, int B, int C, int HW) {
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(out.is_contiguous() && out.size(-1) % 8 == 0);
+  check(pa::nchw_to_nhwc_pad(reinterpret_cast<const void*>(x_ptr), out.data_ptr(), B, C, HW, (int)out.size(-1),
+                             cur_stream()), "nchw_to_nhwc_pad");
+}
+
+static void upsample2x(Tensor x, Tensor out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 4 && x.is_contiguous() && out.is_contiguous(), "x must be NHWC [B, H, W, C]");
+  check(pa::upsample_nearest2x_nhwc(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                                    (int)x.size(3), cur_stream()), "upsample2x");
+}
+
+static void concat_channels(Tensor a, Tensor b, Tensor out) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && out.is_contiguous());
+  const long long rows = a.numel() / a.size(-1);
+  TORCH_CHECK(b.numel() / b.size(-1) == rows, "concat: row mismatch");
+  check(pa::concat_channels(a.data_ptr(), b.data_ptr(), out.data_ptr(), rows, (int)a.size(-1), (int)b.size(-1),
+                            cur_stream()), "concat_channels");
+}
+
+static void unet_out_gather(Tensor eps, c10::optional<Tensor> x, uintptr_t x_out_ptr, c10::optional<Tensor> sigmas,
+                            int n, int C, bool cfg_pairs, double cfg, int mode, long long out_sample_off) {
+  c10::cuda::CUDAGuard guard(eps.device());
+  TORCH_CHECK(eps.dim() == 3 && eps.is_contiguous(), "eps must be [B, HW, Cpad]");
+  TORCH_CHECK(mode == 0 || (x && sigmas), "Euler update needs x and sigmas");
+  check(pa::unet_out_gather(eps.data_ptr(), x ? x->data_ptr() : nullptr, reinterpret_cast<void*>(x_out_ptr),
+                            sigmas ? sigmas->data_ptr() : nullptr, n, C, (int)eps.size(1), (int)eps.size(2),
+                            cfg_pairs ? 1 : 0, (float)cfg, mode, out_sample_off, cur_stream()),
+        "unet_out_gather");
+}
+
+static void rms_rope(Tensor x, Tensor w, c10::optional<Tensor> rope, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  int b, rows;
+  long long ld, bs;
+  view3(x, b, rows, ld, bs);
+  if (rope) TORCH_CHECK(rope->scalar_type() == at::kFloat && rope->is_contiguous() && rope->size(-1) == 2 &&
+                        rope->size(-2) == 64 && rope->size(0) >= rows, "rope must be float32 [L, 64, 2]");
+  check(pa::rms_rope_inplace(x.data_ptr(), ld, bs, w.data_ptr(), rope ? rope->data_ptr() : nullptr, b, rows,
+                             (int)x.size(-1), (float)eps, cur_stream()), "rms_rope");
+}
+
+static void bcast_add(Tensor a, Tensor m, Tensor out) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.dim() == 2 && m.dim() == 2 && a.size(1) == m.size(1) && a.is_contiguous() && m.is_contiguous() &&
+              out.is_contiguous());
+  check(pa::bcast_add(a.data_ptr(), m.data_ptr(), out.data_ptr(), (int)a.size(0), (int)m.size(0), (int)a.size(1),
+                      cur_stream()), "bcast_add");
+}
+
 static void silu_(Tensor x, Tensor out) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && out.is_contiguous());
@@ -278,6 +331,12 @@ PYBIND11_MODULE(_C, m) {
   m.def("timestep_embedding", &timestep_embedding);
   m.def("patchify", &patchify);
   m.def("scatter_patch_embed", &scatter_patch_embed);
+  m.def("nchw_to_nhwc_pad", &nchw_to_nhwc_pad);
+  m.def("upsample2x", &upsample2x);
+  m.def("concat_channels", &concat_channels);
+  m.def("unet_out_gather", &unet_out_gather);
+  m.def("rms_rope", &rms_rope);
+  m.def("bcast_add", &bcast_add);
   m.def("silu", &silu_);
   m.def("add", &add_);
   m.def("attention", &attention);

@@ -33,6 +33,17 @@ int timestep_embedding(const void* t, void* out, long long ldo, int B, int dim, 
 int patchify(const void* x, void* out, long long ldo, long long o_bstride, int B, int C, int H, int W, int ps,
              cudaStream_t st);
 
+// layout / glue for the convolutional executors (csrc/kernels/layout.cu)
+int nchw_to_nhwc_pad(const void* x, void* out, int B, int C, int HW, int Cpad, cudaStream_t st);
+int upsample_nearest2x_nhwc(const void* x, void* out, int B, int H, int W, int C, cudaStream_t st);
+int concat_channels(const void* a, const void* b, void* out, long long rows, int C1, int C2, cudaStream_t st);
+int unet_out_gather(const void* eps, const void* x, void* x_out, const void* sigmas, int n, int C, int HW, int Cpad,
+                    int cfg_pairs, float cfg, int mode, long long out_sample_off, cudaStream_t st);
+
+int rms_rope_inplace(void* x, long long ldx, long long x_bs, const void* w, const void* rope, int batch, int rows,
+                     int D, float eps, cudaStream_t st);
+int bcast_add(const void* a, const void* m, void* out, int B, int nblk, int n, cudaStream_t st);
+
 // elementwise helpers
 int silu_bf16(const void* x, void* out, long long n, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st);

@@ -134,6 +134,105 @@ int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, 
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ full-width RMSNorm (+ RoPE) in place
+// WAN-style q/k norm: RMS over the whole hidden dim (all heads), learned weight, then per-head RoPE on
+// adjacent pairs with a [L, 64] (cos, sin) table.  One warp per row, row held in registers.
+template <int MAX_VEC>
+__global__ void __launch_bounds__(256) rms_rope_kernel(__nv_bfloat16* __restrict__ x, long long ldx, long long x_bs,
+                                                       const __nv_bfloat16* __restrict__ w,
+                                                       const float2* __restrict__ rope, int batch, int rows, int D,
+                                                       float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * rows) return;
+  const int b = warp / rows, r = warp - b * rows;
+  uint4* xr = reinterpret_cast<uint4*>(x + b * x_bs + static_cast<long long>(r) * ldx);
+  const int nvec = D >> 3;
+  uint4 buf[MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      buf[i] = xr[idx];
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+    }
+  }
+  ss = warp_sum(ss);
+  const float rr = rsqrtf(ss / D + eps);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float v[8], g[8];
+      unpack8(buf[i], v);
+      unpack8(__ldg(wv + idx), g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = v[e] * rr * g[e];
+      if (rope != nullptr) {
+        const int d0 = (idx * 8) & 127;                      // offset inside the 128-wide head
+        const float4* rp = reinterpret_cast<const float4*>(rope + static_cast<long long>(r) * 64 + (d0 >> 1));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float4 cs = __ldg(rp + j);
+          const float x0 = v[4 * j], x1 = v[4 * j + 1], x2 = v[4 * j + 2], x3 = v[4 * j + 3];
+          v[4 * j] = cs.x * x0 - cs.y * x1;
+          v[4 * j + 1] = cs.y * x0 + cs.x * x1;
+          v[4 * j + 2] = cs.z * x2 - cs.w * x3;
+          v[4 * j + 3] = cs.w * x2 + cs.z * x3;
+        }
+      }
+      xr[idx] = pack8(v);
+    }
+  }
+}
+
+int rms_rope_inplace(void* x, long long ldx, long long x_bs, const void* w, const void* rope, int batch, int rows,
+                     int D, float eps, cudaStream_t st) {
+  if (D % 128 || ldx % 8 || x_bs % 8) return -1;
+  const long long warps = static_cast<long long>(batch) * rows;
+  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+  auto X = static_cast<__nv_bfloat16*>(x);
+  auto Wt = static_cast<const __nv_bfloat16*>(w);
+  auto R = static_cast<const float2*>(rope);
+  if (D <= 32 * 8 * 4) rms_rope_kernel<4><<<blocks, 256, 0, st>>>(X, ldx, x_bs, Wt, R, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 12) rms_rope_kernel<12><<<blocks, 256, 0, st>>>(X, ldx, x_bs, Wt, R, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 20) rms_rope_kernel<20><<<blocks, 256, 0, st>>>(X, ldx, x_bs, Wt, R, batch, rows, D, eps);
+  else return -2;
+  return (int)cudaGetLastError();
+}
+
+// out[b, i, :] = a[b, :] + m[i, :]     (per-block modulation tables = learned offsets + time projection)
+__global__ void bcast_add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ m, uint4* __restrict__ out,
+                                 int B, int nblk, int nv) {
+  const long long total = static_cast<long long>(B) * nblk * nv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % nv);
+    const long long r = i / nv;
+    const int blk = static_cast<int>(r % nblk);
+    const int b = static_cast<int>(r / nblk);
+    float x[8], y[8];
+    unpack8(__ldg(a + static_cast<long long>(b) * nv + c), x);
+    unpack8(__ldg(m + static_cast<long long>(blk) * nv + c), y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] += y[e];
+    out[i] = pack8(x);
+  }
+}
+
+int bcast_add(const void* a, const void* m, void* out, int B, int nblk, int n, cudaStream_t st) {
+  if (n % 8) return -1;
+  const long long total = static_cast<long long>(B) * nblk * (n / 8);
+  bcast_add_kernel<<<static_cast<int>(pa_min_ll((total + 255) / 256, 148 * 8)), 256, 0, st>>>(
+      static_cast<const uint4*>(a), static_cast<const uint4*>(m), static_cast<uint4*>(out), B, nblk, n / 8);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ timestep embedding
 __global__ void temb_kernel(const void* t, __nv_bfloat16* out, long long ldo, int B, int dim, float time_factor,
                             float max_period, int t_is_bf16) {
