@@ -19,6 +19,13 @@ def builder_for(module: nn.Module) -> Optional[Callable]:
                 and module.params.patch_size == 2:
             from .flux_exec import build_flux_executor
             return build_flux_executor
+    if fam == "wan":
+        from ..models.wan import WanModel
+        p = getattr(module, "params", None)
+        if isinstance(module, WanModel) and p.dim // p.num_heads == 128 and tuple(p.patch_size) == (1, 2, 2) \
+                and p.in_dim == 16:
+            from .wan_exec import build_wan_executor
+            return build_wan_executor
     if fam == "unet":
         from . import unet_exec
         if unet_exec.supports(module):

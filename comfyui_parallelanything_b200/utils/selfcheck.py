@@ -498,3 +498,35 @@ def unet_executor_mini():
     r["euler_mean_rel"] = r2["mean_rel"]
     r["ok"] = r["ok"] and r2["ok"]
     return r
+
+
+@check
+def wan_executor_tiny():
+    from ..exec.wan_exec import WanExecutor
+    from ..models import wan
+    p = wan.wan_tiny_params()
+    torch.manual_seed(2)
+    m = wan.WanModel(p).to(device=_dev(), dtype=torch.bfloat16).eval()
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if "norm" in n_ and n_.endswith("weight"):
+                p_.add_(0.1 * torch.randn_like(p_))
+    ex = WanExecutor(m, _dev())
+    oracle = wan.WanModel(p).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    inp = wan.example_inputs(p, 2, frames=8, height=128, width=192, device=_dev(), dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = ex(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+        eager = m(**inp)
+    r = _cmp("wan_executor_tiny", got, want, 0.03)
+    r["eager_bf16_mean_rel"] = _cmp("eager", eager, want, 1.0)["mean_rel"]
+    r["launches"] = ex.launches_per_step
+    sig = torch.tensor([[1.0, 0.8], [0.6, 0.5]], device=_dev())
+    x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
+    nxt = ex.denoise_step(x, t, c, sig).clone()
+    want2 = inp["x"].float() + (sig[:, 1] - sig[:, 0])[:, None, None, None, None] * want
+    r2 = _cmp("wan_euler", nxt, want2, 0.03)
+    r["euler_mean_rel"] = r2["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
