@@ -78,6 +78,7 @@ class ParallelEngine:
         self._orig_forward = None
         self._cond_cache: Dict[Tuple, Any] = {}
         self._lock = threading.Lock()
+        self._peer_ready = False
         self.active = False
 
     # ------------------------------------------------------------------ setup
@@ -264,6 +265,8 @@ class ParallelEngine:
         k_chunks = sp.split_kwargs(kwargs, act_sizes, batch)
         lead_dev = self.lead_device
         lead_stream = torch.cuda.current_stream(lead_dev) if lead_dev.type == "cuda" else None
+        if self._can_fuse(active, x):
+            return self._data_parallel_fused(step, batch, active, offs, x, t_chunks, c_chunks, k_chunks, lead_stream)
         out_box: Dict[str, Any] = {"buf": None}
         results: List[Any] = [None] * len(active)
         t0 = time.perf_counter()
@@ -323,6 +326,61 @@ class ParallelEngine:
             missing = [active[i][0].name for i, r in enumerate(results) if r is None]
             raise RuntimeError(f"Missing results from devices: {missing}")
         return sp.concatenate_results(results, dim=0)
+
+    # ---- native executors, one process: scatter/gather happen inside the replicas' kernels --------------
+    def _can_fuse(self, active, x) -> bool:
+        if self.config.backend in ("torch", "nccl") or not isinstance(x, torch.Tensor):
+            return False
+        if x.device != self.lead_device or x.device.type != "cuda" or x.dtype != torch.bfloat16 or not x.is_contiguous():
+            return False
+        if not all(getattr(s.replica, "pa_native", False) and hasattr(s.replica, "forward_shard") for s, _ in active):
+            return False
+        if not self._peer_ready:
+            from . import ops
+            C = ops.require()
+            lead = self.lead_device.index
+            ok = all(C.enable_peer_access(s.device.index, lead) for s, _ in active)
+            self._peer_ready = bool(ok)
+        return self._peer_ready
+
+    def _data_parallel_fused(self, step, batch, active, offs, x, t_chunks, c_chunks, k_chunks, lead_stream):
+        """Every replica's FIRST kernel loads its latent shard from ``x`` on the lead GPU (NVLink peer loads)
+        and its LAST kernel stores its output rows at their final offset in ``out`` on the lead GPU; the host
+        only orders streams (no copies of x / the result, no cat, no device-wide sync)."""
+        out = torch.empty_like(x)
+        sample_bytes = x[0].numel() * x.element_size()
+        t0 = time.perf_counter()
+
+        def run(i: int):
+            slot, size = active[i]
+            dev = slot.device
+            pp.set_pipeline_mode(False)
+            faults.check_step(step, slot.name, slot.index)
+            with torch.cuda.device(dev), torch.cuda.stream(slot.stream):
+                slot.stream.wait_stream(lead_stream)
+                t_in = sp.move_to_device(t_chunks[i], dev, non_blocking=True)
+                c_in = self._cached_move(("ctx", i), c_chunks[i], dev)
+                k_in = {k: sp.move_to_device(v, dev, non_blocking=True) for k, v in k_chunks[i].items()}
+                shape = (size,) + tuple(x.shape[1:])
+                slot.replica.forward_shard(x.data_ptr() + offs[i] * sample_bytes, shape, t_in, c_in,
+                                           out.data_ptr(), offs[i], **k_in)
+                lead_stream.wait_stream(slot.stream)
+            return None
+
+        futures = [active[i][0].worker.submit(lambda i=i: run(i)) for i in range(len(active))]
+        errors = []
+        for i, f in enumerate(futures):
+            try:
+                f.result()
+            except BaseException as e:  # noqa: BLE001
+                errors.append((active[i][0].name, e))
+        if errors:
+            for name, e in errors:
+                log.error("on %s: %s", name, e)
+            raise errors[0][1]
+        self.metrics.record(step=step, host_ms=(time.perf_counter() - t0) * 1e3, batch=batch,
+                            sizes=[z for _, z in active], fused=True)
+        return out
 
     def _cached_move(self, key, value, dev):
         """Conditioning is constant across the steps of one sampling run; re-use the

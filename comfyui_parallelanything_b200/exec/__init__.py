@@ -26,6 +26,11 @@ def builder_for(module: nn.Module) -> Optional[Callable]:
                 and p.in_dim == 16:
             from .wan_exec import build_wan_executor
             return build_wan_executor
+    if fam == "vae":
+        from ..models.vae import VAEDecoder
+        if isinstance(module, VAEDecoder):
+            from .vae_exec import build_vae_executor
+            return build_vae_executor
     if fam == "unet":
         from . import unet_exec
         if unet_exec.supports(module):

@@ -261,6 +261,20 @@ class FluxExecutor(nn.Module):
             return out
 
     @torch.no_grad()
+    def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, y=None,
+                      guidance=None, **_ignored):
+        """In-process multi-GPU path: pull this replica's latent shard from the lead GPU's tensor (peer
+        pointer) inside the first kernel and store the velocity rows straight into the lead's output."""
+        with torch.cuda.device(self.device):
+            B = shape[0]
+            dummy = torch.empty(0, device=self.device)
+            _, timesteps, context, y, guidance = self._prep(dummy.new_empty((B, 1, 1, 1), dtype=torch.bfloat16),
+                                                             timesteps, context, y, guidance)
+            ws = self.workspace(B, shape[2], shape[3], context.shape[1])
+            self._run(ws, x_src_ptr, timesteps, context, y, guidance, None, out_ptr=out_ptr,
+                      out_sample_off=out_sample_off)
+
+    @torch.no_grad()
     def denoise_step(self, x, timesteps, context, y, guidance, sigmas, out=None, out_ptr=None, out_sample_off=0,
                      x_src_ptr: Optional[int] = None, t_src_ptr: Optional[int] = None,
                      g_src_ptr: Optional[int] = None):

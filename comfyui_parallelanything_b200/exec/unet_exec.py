@@ -282,6 +282,17 @@ class UNetExecutor(nn.Module):
             return out
 
     @torch.no_grad()
+    def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, y=None,
+                      **_ignored):
+        with torch.cuda.device(self.device):
+            d = self.device
+            bf = lambda t: t.to(device=d, dtype=torch.bfloat16).contiguous()  # noqa: E731
+            eps = self._eps_nhwc(x_src_ptr, shape[0], shape[2], shape[3], bf(timesteps), bf(context),
+                                 bf(y) if y is not None else None)
+            ops.require().unet_out_gather(eps, None, out_ptr, None, shape[0], self.out_ch, False, 1.0, 0,
+                                          out_sample_off)
+
+    @torch.no_grad()
     def denoise_step(self, x, timesteps, context, y, sigmas, cfg_scale: float = 1.0, cfg_pairs: bool = False,
                      out=None, out_ptr: Optional[int] = None, out_sample_off: int = 0,
                      x_src_ptr: Optional[int] = None):

@@ -206,6 +206,15 @@ class WanExecutor(nn.Module):
             return out
 
     @torch.no_grad()
+    def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, **_ignored):
+        with torch.cuda.device(self.device):
+            d = self.device
+            timesteps = timesteps.to(device=d, dtype=torch.bfloat16).contiguous()
+            context = context.to(device=d, dtype=torch.bfloat16).contiguous()
+            ws = self.workspace(shape[0], shape[2], shape[3], shape[4], context.shape[1])
+            self._run(ws, x_src_ptr, timesteps, context, None, out_ptr=out_ptr, out_sample_off=out_sample_off)
+
+    @torch.no_grad()
     def denoise_step(self, x, timesteps, context, sigmas, out=None, out_ptr=None, out_sample_off=0,
                      x_src_ptr: Optional[int] = None, t_src_ptr: Optional[int] = None):
         with torch.cuda.device(self.device):

@@ -530,3 +530,20 @@ def wan_executor_tiny():
     r["euler_mean_rel"] = r2["mean_rel"]
     r["ok"] = r["ok"] and r2["ok"]
     return r
+
+
+@check
+def vae_decoder_executor():
+    from ..exec.vae_exec import VAEDecoderExecutor
+    from ..models import vae
+    torch.manual_seed(4)
+    cfg = dict(z_channels=4, ch=64, ch_mult=[1, 2], num_res_blocks=1, out_ch=3)
+    m = vae.VAEDecoder(**cfg).to(device=_dev(), dtype=torch.bfloat16).eval()
+    ex = VAEDecoderExecutor(m, _dev())
+    oracle = vae.VAEDecoder(**cfg).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    z = _rand(2, 4, 16, 24, scale=0.18)
+    with torch.no_grad():
+        got = ex.decode(z)
+        want = oracle(z.float())
+    return _cmp("vae_decoder_executor", got, want, 0.03)

@@ -256,6 +256,13 @@ static void bcast_add(Tensor a, Tensor m, Tensor out) {
                       cur_stream()), "bcast_add");
 }
 
+static void softmax_rows(Tensor x, double scale) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && x.scalar_type() == at::kBFloat16);
+  check(pa::softmax_rows(x.data_ptr(), x.stride(0), (int)x.size(0), (int)x.size(1), (float)scale, cur_stream()),
+        "softmax_rows");
+}
+
 static void silu_(Tensor x, Tensor out) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.is_contiguous() && out.is_contiguous());
@@ -337,6 +344,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("unet_out_gather", &unet_out_gather);
   m.def("rms_rope", &rms_rope);
   m.def("bcast_add", &bcast_add);
+  m.def("softmax_rows", &softmax_rows);
   m.def("silu", &silu_);
   m.def("add", &add_);
   m.def("attention", &attention);

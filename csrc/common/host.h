@@ -44,6 +44,8 @@ int rms_rope_inplace(void* x, long long ldx, long long x_bs, const void* w, cons
                      int D, float eps, cudaStream_t st);
 int bcast_add(const void* a, const void* m, void* out, int B, int nblk, int n, cudaStream_t st);
 
+int softmax_rows(void* x, long long ld, int rows, int n, float scale, cudaStream_t st);
+
 // elementwise helpers
 int silu_bf16(const void* x, void* out, long long n, cudaStream_t st);
 int add_bf16(const void* a, const void* b, void* out, long long n, cudaStream_t st);

@@ -233,6 +233,58 @@ int bcast_add(const void* a, const void* m, void* out, int B, int nblk, int n, c
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ row softmax (in place, bf16)
+// One CTA per row; used by the VAE's single-head 512-wide attention, which is evaluated as
+// GEMM -> softmax -> GEMM on the tensor cores (it runs once per image, not per denoise step).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(__nv_bfloat16* __restrict__ x, long long ld, int n,
+                                                           float scale_log2) {
+  __shared__ float red[8];
+  uint4* row = reinterpret_cast<uint4*>(x + static_cast<long long>(blockIdx.x) * ld);
+  const int nv = n >> 3;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float v[8];
+    unpack8(row[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[e]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float v[8];
+    unpack8(row[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += exp2f((v[e] - mx) * scale_log2);
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    float v[8];
+    unpack8(row[i], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = exp2f((v[e] - mx) * scale_log2) * inv;
+    row[i] = pack8(v);
+  }
+}
+
+int softmax_rows(void* x, long long ld, int rows, int n, float scale, cudaStream_t st) {
+  if (n % 8 || ld % 8) return -1;
+  softmax_rows_kernel<<<rows, 256, 0, st>>>(static_cast<__nv_bfloat16*>(x), ld, n, scale * 1.4426950408889634f);
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ timestep embedding
 __global__ void temb_kernel(const void* t, __nv_bfloat16* out, long long ldo, int B, int dim, float time_factor,
                             float max_period, int t_is_bf16) {
