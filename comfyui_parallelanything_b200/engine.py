@@ -238,6 +238,8 @@ class ParallelEngine:
                     return self._replica_call(lead.replica, x, timesteps, context=context, **kwargs)
             if batch < n or not self.config.workload_split:
                 return self._lead_only(x, timesteps, context, kwargs)
+            if self.config.pair_cfg and batch % 2 == 0 and batch // 2 >= n:
+                return self._forward_cfg_paired(step, batch, x, timesteps, context, kwargs)
             sizes = self.split_sizes(batch)
             active = [(s, z) for s, z in zip(self.slots, sizes) if z > 0]
             if not active:
@@ -255,6 +257,46 @@ class ParallelEngine:
             raise
 
     __call__ = forward
+
+    def _forward_cfg_paired(self, step, batch, x, timesteps, context, kwargs):
+        """CFG-aware split (SURVEY §2.3 "CFG parallel"): ComfyUI hands the sampler's cond and uncond halves as
+        one 2B batch; the reference splits it blindly, so a sample's two halves usually land on different
+        devices.  Here sample i and i + B/2 always travel together (so a replica can apply
+        ``uncond + s*(cond - uncond)`` locally and ship half the bytes back)."""
+        half = batch // 2
+        pair_sizes = self.split_sizes(half)
+        idx, sizes = [], []
+        off = 0
+        for z in pair_sizes:
+            idx += list(range(off, off + z)) + list(range(half + off, half + off + z))
+            sizes.append(2 * z)
+            off += z
+        dev = x.device if isinstance(x, torch.Tensor) else None
+        perm = torch.tensor(idx, dtype=torch.long, device=dev)
+
+        def pick(v):
+            if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == batch:
+                return v.index_select(0, perm.to(v.device))
+            if isinstance(v, (list, tuple)):
+                return type(v)(pick(t) for t in v)
+            if isinstance(v, dict):
+                return {k: pick(t) for k, t in v.items()}
+            return v
+        active = [(s, z) for s, z in zip(self.slots, sizes) if z > 0]
+        if len(active) == 1:
+            return self._lead_only(x, timesteps, context, kwargs)
+        out_p = self._data_parallel(step, batch, active, pick(x), pick(timesteps), pick(context), pick(kwargs))
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(batch, device=perm.device)
+
+        def unpick(v):
+            if isinstance(v, torch.Tensor):
+                return v.index_select(0, inv.to(v.device))
+            if isinstance(v, (list, tuple)):
+                return type(v)(unpick(t) for t in v)
+            return v
+        self.metrics.incr("cfg_paired_steps")
+        return unpick(out_p)
 
     def _data_parallel(self, step: int, batch: int, active, x, timesteps, context, kwargs):
         act_sizes = [z for _, z in active]

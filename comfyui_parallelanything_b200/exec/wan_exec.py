@@ -73,7 +73,12 @@ class WanExecutor(nn.Module):
         W["mod_table"] = torch.stack(mods, 0).contiguous()                               # [n_blocks, 6*dim]
         hm = _bf(model.head.modulation.reshape(2, p.dim), d)
         W["head_shift"], W["head_scale"] = hm[0:1].contiguous(), hm[1:2].contiguous()
-        lin("head", model.head.head)
+        # WAN's head emits features ordered (pt, ph, pw, c); the fused unpatchify epilogue expects (c, ph, pw):
+        # permute the rows once at build time instead of shuffling activations every step.
+        hw_, hb_ = model.head.head.weight.detach(), model.head.head.bias.detach()
+        oc = p.out_dim
+        W["head.w"] = _bf(hw_.view(4, oc, p.dim).permute(1, 0, 2).reshape(4 * oc, p.dim), d)
+        W["head.b"] = _bf(hb_.view(4, oc).permute(1, 0).reshape(4 * oc), d)
         self.W = W
         self.n_blocks = len(model.blocks)
         self.eps = p.eps
@@ -156,14 +161,27 @@ class WanExecutor(nn.Module):
         def mod(i, j):
             return MOD[:, i, j * dim:(j + 1) * dim]
 
+        dbg = getattr(self, "_dbg", None)
+        if dbg is not None:
+            dbg.update(x0=X.clone(), e=ws["E"].clone(), e0=ws["E0"].clone(), ctx=ws["CTX"].clone())
         for i in range(self.n_blocks):
             # ---- self attention
             ops.layernorm_modulate(X, XM, scale=mod(i, 1), shift=mod(i, 0), eps=self.eps)
+            if dbg is not None and i == 0:
+                dbg["xm0"] = XM.clone()
             ops.gemm(XM, W[f"b{i}.qkv.w"], "bias", out=QKV, bias=W[f"b{i}.qkv.b"])
+            if dbg is not None and i == 0:
+                dbg["qkv_raw"] = QKV.clone()
             C.rms_rope(QKV[:, :, :dim], W[f"b{i}.nq"], ROPE, self.eps)
             C.rms_rope(QKV[:, :, dim:2 * dim], W[f"b{i}.nk"], ROPE, self.eps)
+            if dbg is not None and i == 0:
+                dbg["qkv_rope"] = QKV.clone()
             ops.attention(self._heads(QKV, 0, 3), self._heads(QKV, 1, 3), self._heads(QKV, 2, 3), out=ATT)
+            if dbg is not None and i == 0:
+                dbg["att"] = ATT.clone()
             ops.gemm(ATT, W[f"b{i}.o.w"], "gate_res", out=X, residual=X, gate=mod(i, 2), bias=W[f"b{i}.o.b"])
+            if dbg is not None and i == 0:
+                dbg["x_sa"] = X.clone()
             # ---- text cross attention
             ops.layernorm_modulate(X, XM, gamma=W[f"b{i}.n3.g"], beta=W[f"b{i}.n3.b"], eps=self.eps)
             ops.gemm(XM, W[f"b{i}.cq.w"], "bias", out=ws["CQ"], bias=W[f"b{i}.cq.b"])
@@ -171,10 +189,14 @@ class WanExecutor(nn.Module):
             ops.attention(self._heads(ws["CQ"], 0, 1), self._heads(ws["CKV"][i], 0, 2), self._heads(ws["CKV"][i], 1, 2),
                           out=ATT)
             ops.gemm(ATT, W[f"b{i}.co.w"], "res", out=X, residual=X, bias=W[f"b{i}.co.b"])
+            if dbg is not None and i == 0:
+                dbg["x_ca"] = X.clone()
             # ---- FFN
             ops.layernorm_modulate(X, XM, scale=mod(i, 4), shift=mod(i, 3), eps=self.eps)
             ops.gemm(XM, W[f"b{i}.f0.w"], "gelu", out=FF, bias=W[f"b{i}.f0.b"])
             ops.gemm(FF, W[f"b{i}.f2.w"], "gate_res", out=X, residual=X, gate=mod(i, 5), bias=W[f"b{i}.f2.b"])
+            if dbg is not None and i == 0:
+                dbg["x_b0"] = X.clone()
             n += 14
         # ---- head: AdaLN + Linear + unpatchify (+ Euler, + peer store)
         ops.layernorm_modulate(X, XM, scale=ws["HSCALE"][:, 0], shift=ws["HSHIFT"][:, 0], eps=self.eps)

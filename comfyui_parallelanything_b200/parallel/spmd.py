@@ -262,3 +262,69 @@ class SpmdFluxEngine:
         dist.barrier()
         self.buf, self.flags = {}, None
         self.heap.close()
+
+
+def broadcast_executor_weights(executor, src: int = 0, group=None, bucket_bytes: int = 256 << 20) -> int:
+    """Weight replication over NVLink for the one-process-per-GPU layout: rank ``src`` holds the
+    packed weights, every other rank receives them device-to-device through NCCL broadcasts (NVSwitch
+    multicast / NVLS when NCCL enables it) in ``bucket_bytes`` buckets — no host bounce, unlike the
+    reference's ``source.cpu()`` + per-key H2D clone (/root/reference/any_device_parallel.py:600-663).
+    Returns the number of bytes received/sent."""
+    tensors = [t for t in _executor_tensors(executor) if t is not None and t.is_cuda]
+    total, bucket, size = 0, [], 0
+
+    def flush():
+        nonlocal bucket, size, total
+        if not bucket:
+            return
+        flat = torch.cat([t.reshape(-1).view(torch.uint8) for t in bucket]) if len(bucket) > 1 \
+            else bucket[0].reshape(-1).view(torch.uint8)
+        dist.broadcast(flat, src=src, group=group)
+        if dist.get_rank(group) != src and len(bucket) > 1:
+            off = 0
+            for t in bucket:
+                n = t.numel() * t.element_size()
+                t.reshape(-1).view(torch.uint8).copy_(flat[off:off + n])
+                off += n
+        total += flat.numel()
+        bucket, size = [], 0
+
+    for t in tensors:
+        n = t.numel() * t.element_size()
+        if n >= bucket_bytes:                 # big tensors go alone, in place (no staging copy)
+            flush()
+            dist.broadcast(t, src=src, group=group)
+            total += n
+            continue
+        bucket.append(t)
+        size += n
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return total
+
+
+def _executor_tensors(executor):
+    w = getattr(executor, "W", None)
+    if isinstance(w, dict):
+        for k in sorted(w):
+            yield w[k]
+        return
+    seen = set()
+
+    def walk(o):
+        if isinstance(o, torch.Tensor):
+            if id(o) not in seen:
+                seen.add(id(o))
+                yield o
+        elif isinstance(o, (list, tuple)):
+            for v in o:
+                yield from walk(v)
+        elif isinstance(o, dict):
+            for k in sorted(o, key=str):
+                yield from walk(o[k])
+        elif hasattr(o, "__dict__") and not isinstance(o, (torch.nn.Module, type)):
+            yield from walk(vars(o))
+    for name in sorted(vars(executor)):
+        if not name.startswith("_"):
+            yield from walk(getattr(executor, name))

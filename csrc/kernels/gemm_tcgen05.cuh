@@ -87,6 +87,197 @@ __device__ __forceinline__ void acc8(const uint32_t (&r)[32], int g, const __nv_
   }
 }
 
+// Fused epilogue of one accumulator tile (thread == accumulator row `row` of batch `b`; `taddr` = this warp's
+// TMEM lane quadrant + accumulator column base; `n0` = first output column of the tile).  Shared by the bf16 and
+// the block-scaled fp8 mainloops.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int b, int row, bool row_ok,
+                                              int n0) {
+  if (p.mode == EPI_QKV_ROPE) {
+    const int qkv_cols = 3 * p.heads * 128;
+#pragma unroll 1
+    for (int hg = 0; hg < BN / 128; ++hg) {
+      const int ng = n0 + hg * 128;
+      if (ng >= p.N) break;
+      if (ng < qkv_cols) {
+        const int sec = ng / (p.heads * 128);
+        const int head = (ng - sec * p.heads * 128) >> 7;
+        float rrms = 1.0f;
+        if (sec < 2) {
+          float ss = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float x[8];
+              acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ss += x[e] * x[e];
+            }
+          }
+          rrms = rsqrtf(ss * (1.0f / 128.0f) + p.qk_eps);
+        }
+        __nv_bfloat16* dst_base = (sec == 0 ? p.q : (sec == 1 ? p.k : p.v));
+        const long long pos = p.seq_off + row;
+        __nv_bfloat16* dst = dst_base + ((static_cast<long long>(b) * p.heads + head) * p.seq_total + pos) * 128;
+        const __nv_bfloat16* nw = sec == 0 ? p.q_scale : p.k_scale;
+        const bool do_rope = sec < 2 && p.rope != nullptr && row_ok;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float x[8];
+            acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
+            if (sec < 2) {
+              float w[8];
+              ldg8(nw + c * 32 + g * 8, w);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = x[e] * rrms * w[e];
+              if (do_rope) {
+                const float4* rp = reinterpret_cast<const float4*>(p.rope + pos * 64 + c * 16 + g * 4);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const float4 cs = __ldg(rp + j);     // (cos0, sin0, cos1, sin1)
+                  const float x0 = x[4 * j], x1 = x[4 * j + 1], x2 = x[4 * j + 2], x3 = x[4 * j + 3];
+                  x[4 * j] = cs.x * x0 - cs.y * x1;
+                  x[4 * j + 1] = cs.y * x0 + cs.x * x1;
+                  x[4 * j + 2] = cs.z * x2 - cs.w * x3;
+                  x[4 * j + 3] = cs.w * x2 + cs.z * x3;
+                }
+              }
+            }
+            if (row_ok) st8(dst + c * 32 + g * 8, x);
+          }
+        }
+      } else {
+        // GELU'd MLP columns of a FLUX single block -> concat buffer
+        const long long col = p.mlp_col_off + (ng - qkv_cols);
+        __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc + col;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float x[8];
+            acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(x[e]);
+            if (row_ok) st8(orow + c * 32 + g * 8, x);
+          }
+        }
+      }
+    }
+  } else if (p.mode == EPI_EULER_UNPATCH) {
+    // token `row` = (hh, ww) of the patch grid; column n = (c, ph, pw), ps == 2.
+    const int Wp = p.Wl / p.ps;
+    const int hh = row / Wp, ww = row - hh * Wp;
+    const bool euler = p.sigmas != nullptr;
+    float dt = 0.f;
+    if (euler) dt = p.sigmas[2 * b + 1] - p.sigmas[2 * b];
+    const long long sample_elems = static_cast<long long>(p.C) * p.Hl * p.Wl;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      if (n0 + c * 32 >= p.N) break;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float x[8];
+        acc8(r, g, p.bias ? p.bias + n0 + c * 32 + g * 8 : nullptr, x);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {     // (pw = 0, 1) are adjacent pixels -> one 4-byte store
+            const int n = n0 + c * 32 + g * 8 + j;
+            const int ch = n >> 2, ph = (n >> 1) & 1;
+            const long long pix = (static_cast<long long>(ch) * p.Hl + (hh * 2 + ph)) * p.Wl + ww * 2;
+            float v0 = x[j], v1 = x[j + 1];
+            if (euler) {
+              const float2 xi = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.x_in + b * sample_elems + pix));
+              v0 = xi.x + dt * v0;
+              v1 = xi.y + dt * v1;
+            }
+            *reinterpret_cast<uint32_t*>(p.x_out + (p.xout_sample_off + b) * sample_elems + pix) =
+                pack_bf16(v0, v1);
+          }
+        }
+      }
+    }
+  } else if (p.mode == EPI_GEGLU) {
+    // columns come in groups of 64 = [a(32) | g(32)]; output column = n/2
+    __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;
+#pragma unroll 1
+    for (int c = 0; c < BN / 64; ++c) {
+      const int n = n0 + c * 64;
+      if (n >= p.N) break;
+      uint32_t ra[32], rg[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 64, ra);
+      ptx::tmem_ld_32x32b_x32(taddr + c * 64 + 32, rg);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float a[8], gt[8];
+        acc8(ra, g, p.bias ? p.bias + n + g * 8 : nullptr, a);
+        acc8(rg, g, p.bias ? p.bias + n + 32 + g * 8 : nullptr, gt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = a[e] * gelu_erf(gt[e]);
+        if (row_ok) st8(orow + n / 2 + g * 8, a);
+      }
+    }
+  } else {
+    __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;
+    const __nv_bfloat16* rrow =
+        p.residual ? p.residual + b * p.res_bstride + static_cast<long long>(row) * p.ldr : nullptr;
+    const __nv_bfloat16* grow = p.gate ? p.gate + b * p.gate_bstride : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n = n0 + c * 32;
+      if (n >= p.N) break;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float x[8];
+        acc8(r, g, p.bias ? p.bias + n + g * 8 : nullptr, x);
+        if (p.mode == EPI_BIAS_GELU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(x[e]);
+        } else if (p.mode == EPI_BIAS_SILU) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = silu(x[e]);
+        } else if (p.mode == EPI_BIAS_BCAST) {
+          float gv[8];
+          ldg8(grow + n + g * 8, gv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] += gv[e];
+        } else if ((p.mode == EPI_GATE_RES || p.mode == EPI_RES) && row_ok) {
+          float res[8];
+          ld8(rrow + n + g * 8, res);
+          if (p.mode == EPI_GATE_RES) {
+            float gv[8];
+            ldg8(grow + n + g * 8, gv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = res[e] + gv[e] * x[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = res[e] + x[e];
+          }
+        }
+        if (row_ok) st8(orow + n + g * 8, x);
+      }
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -234,189 +425,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
 
-      if (p.mode == EPI_QKV_ROPE) {
-        const int qkv_cols = 3 * p.heads * 128;
-#pragma unroll 1
-        for (int hg = 0; hg < BN / 128; ++hg) {
-          const int ng = n0 + hg * 128;
-          if (ng >= p.N) break;
-          if (ng < qkv_cols) {
-            const int sec = ng / (p.heads * 128);
-            const int head = (ng - sec * p.heads * 128) >> 7;
-            float rrms = 1.0f;
-            if (sec < 2) {
-              float ss = 0.f;
-#pragma unroll 1
-              for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
-                ptx::tmem_ld_wait();
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  float x[8];
-                  acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) ss += x[e] * x[e];
-                }
-              }
-              rrms = rsqrtf(ss * (1.0f / 128.0f) + p.qk_eps);
-            }
-            __nv_bfloat16* dst_base = (sec == 0 ? p.q : (sec == 1 ? p.k : p.v));
-            const long long pos = p.seq_off + row;
-            __nv_bfloat16* dst = dst_base + ((static_cast<long long>(b) * p.heads + head) * p.seq_total + pos) * 128;
-            const __nv_bfloat16* nw = sec == 0 ? p.q_scale : p.k_scale;
-            const bool do_rope = sec < 2 && p.rope != nullptr && row_ok;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t r[32];
-              ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float x[8];
-                acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
-                if (sec < 2) {
-                  float w[8];
-                  ldg8(nw + c * 32 + g * 8, w);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) x[e] = x[e] * rrms * w[e];
-                  if (do_rope) {
-                    const float4* rp = reinterpret_cast<const float4*>(p.rope + pos * 64 + c * 16 + g * 4);
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      const float4 cs = __ldg(rp + j);     // (cos0, sin0, cos1, sin1)
-                      const float x0 = x[4 * j], x1 = x[4 * j + 1], x2 = x[4 * j + 2], x3 = x[4 * j + 3];
-                      x[4 * j] = cs.x * x0 - cs.y * x1;
-                      x[4 * j + 1] = cs.y * x0 + cs.x * x1;
-                      x[4 * j + 2] = cs.z * x2 - cs.w * x3;
-                      x[4 * j + 3] = cs.w * x2 + cs.z * x3;
-                    }
-                  }
-                }
-                if (row_ok) st8(dst + c * 32 + g * 8, x);
-              }
-            }
-          } else {
-            // GELU'd MLP columns of a FLUX single block -> concat buffer
-            const long long col = p.mlp_col_off + (ng - qkv_cols);
-            __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc + col;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              uint32_t r[32];
-              ptx::tmem_ld_32x32b_x32(taddr + hg * 128 + c * 32, r);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                float x[8];
-                acc8(r, g, p.bias ? p.bias + ng + c * 32 + g * 8 : nullptr, x);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(x[e]);
-                if (row_ok) st8(orow + c * 32 + g * 8, x);
-              }
-            }
-          }
-        }
-      } else if (p.mode == EPI_EULER_UNPATCH) {
-        // token `row` = (hh, ww) of the patch grid; column n = (c, ph, pw), ps == 2.
-        const int Wp = p.Wl / p.ps;
-        const int hh = row / Wp, ww = row - hh * Wp;
-        const bool euler = p.sigmas != nullptr;
-        float dt = 0.f;
-        if (euler) dt = p.sigmas[2 * b + 1] - p.sigmas[2 * b];
-        const long long sample_elems = static_cast<long long>(p.C) * p.Hl * p.Wl;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          if (n0 + c * 32 >= p.N) break;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float x[8];
-            acc8(r, g, p.bias ? p.bias + n0 + c * 32 + g * 8 : nullptr, x);
-            if (row_ok) {
-#pragma unroll
-              for (int j = 0; j < 8; j += 2) {     // (pw = 0, 1) are adjacent pixels -> one 4-byte store
-                const int n = n0 + c * 32 + g * 8 + j;
-                const int ch = n >> 2, ph = (n >> 1) & 1;
-                const long long pix = (static_cast<long long>(ch) * p.Hl + (hh * 2 + ph)) * p.Wl + ww * 2;
-                float v0 = x[j], v1 = x[j + 1];
-                if (euler) {
-                  const float2 xi = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.x_in + b * sample_elems + pix));
-                  v0 = xi.x + dt * v0;
-                  v1 = xi.y + dt * v1;
-                }
-                *reinterpret_cast<uint32_t*>(p.x_out + (p.xout_sample_off + b) * sample_elems + pix) =
-                    pack_bf16(v0, v1);
-              }
-            }
-          }
-        }
-      } else if (p.mode == EPI_GEGLU) {
-        // columns come in groups of 64 = [a(32) | g(32)]; output column = n/2
-        __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          const int n = n0 + c * 64;
-          if (n >= p.N) break;
-          uint32_t ra[32], rg[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c * 64, ra);
-          ptx::tmem_ld_32x32b_x32(taddr + c * 64 + 32, rg);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float a[8], gt[8];
-            acc8(ra, g, p.bias ? p.bias + n + g * 8 : nullptr, a);
-            acc8(rg, g, p.bias ? p.bias + n + 32 + g * 8 : nullptr, gt);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a[e] = a[e] * gelu_erf(gt[e]);
-            if (row_ok) st8(orow + n / 2 + g * 8, a);
-          }
-        }
-      } else {
-        __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;
-        const __nv_bfloat16* rrow =
-            p.residual ? p.residual + b * p.res_bstride + static_cast<long long>(row) * p.ldr : nullptr;
-        const __nv_bfloat16* grow = p.gate ? p.gate + b * p.gate_bstride : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n = n0 + c * 32;
-          if (n >= p.N) break;
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float x[8];
-            acc8(r, g, p.bias ? p.bias + n + g * 8 : nullptr, x);
-            if (p.mode == EPI_BIAS_GELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(x[e]);
-            } else if (p.mode == EPI_BIAS_SILU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] = silu(x[e]);
-            } else if (p.mode == EPI_BIAS_BCAST) {
-              float gv[8];
-              ldg8(grow + n + g * 8, gv);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) x[e] += gv[e];
-            } else if ((p.mode == EPI_GATE_RES || p.mode == EPI_RES) && row_ok) {
-              float res[8];
-              ld8(rrow + n + g * 8, res);
-              if (p.mode == EPI_GATE_RES) {
-                float gv[8];
-                ldg8(grow + n + g * 8, gv);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = res[e] + gv[e] * x[e];
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = res[e] + x[e];
-              }
-            }
-            if (row_ok) st8(orow + n + g * 8, x);
-          }
-        }
-      }
+      epilogue_tile<BN>(p, taddr, b, row, row_ok, n0);
       // accumulator drained: hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();

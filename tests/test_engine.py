@@ -210,3 +210,28 @@ def test_baseline_config1_sd15_shape_two_cpu_replicas():
     with torch.no_grad():
         assert torch.allclose(m(x, t, context=ctx), plain(x, t, context=ctx), atol=1e-5)
     pa.cleanup_parallel_model(m)
+
+
+def test_cfg_paired_split_keeps_pairs_together():
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    m, plain = Toy(), Toy()
+    plain.load_state_dict(m.state_dict())
+    seen = []
+    orig = Toy.forward
+
+    def spy(self, x, timesteps, context=None, y=None, **kw):
+        seen.append(x[:, 0].clone())
+        return orig(self, x, timesteps, context=context, y=y, **kw)
+    m.forward = spy.__get__(m, Toy)
+    cfg = EngineConfig(pair_cfg=True)
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 25, 25), config=cfg)
+    B = 8                                            # 4 samples: cond rows 0..3, uncond rows 4..7
+    x, t, c, y = inputs(B)
+    x[:, 0] = torch.arange(B, dtype=torch.float32)   # tag rows with their index
+    with torch.no_grad():
+        got = m(x, t, context=c, y=y)
+    assert torch.allclose(got, plain(x, t, context=c, y=y), atol=1e-6)
+    chunks = sorted([s.tolist() for s in seen], key=lambda r: r[0])
+    assert chunks == [[0.0, 1.0, 4.0, 5.0], [2.0, 6.0], [3.0, 7.0]], chunks
+    assert m._parallel_engine.metrics.counters["cfg_paired_steps"] == 1
+    pa.cleanup_parallel_model(m)

@@ -1,0 +1,89 @@
+"""The ComfyUI-facing path on real GPUs: ParallelAnything.setup_parallel -> native sm_100a executors behind
+the hooked forward, single GPU and (when available) multi-GPU with in-kernel NVLink scatter/gather."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+import comfyui_parallelanything_b200 as pa
+from comfyui_parallelanything_b200.models import flux, unet
+
+pytestmark = pytest.mark.gpu
+
+
+def _chain(devs, pcts=None):
+    c = None
+    for i, d in enumerate(devs):
+        c = pa.ParallelDevice().add_device(d, (pcts or [100.0 / len(devs)] * len(devs))[i], c)[0]
+    return c
+
+
+def _flux_case(devs, pcts=None, batch=4):
+    torch.manual_seed(0)
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=512,
+                        mlp_ratio=4.0, num_heads=4, depth=1, depth_single_blocks=2)
+    m = flux.Flux(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    out, = pa.ParallelAnything().setup_parallel(m, _chain(devs, pcts))
+    assert out is m and m._true_parallel_active
+    eng = m._parallel_engine
+    assert all(getattr(r, "pa_native", False) for r in eng.replicas.values()), "expected native executors on B200"
+    inp = flux.example_inputs(p, batch, 256, 256, txt_len=64, device=devs[0], dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = m(inp["x"], inp["timesteps"], context=inp["context"], y=inp["y"], guidance=inp["guidance"])
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+    torch.cuda.synchronize()
+    rel = (got.float() - want).abs().mean().item() / want.abs().mean().item()
+    pa.cleanup_parallel_model(m)
+    return rel, eng
+
+
+def test_single_gpu_native_flux():
+    rel, _ = _flux_case(["cuda:0"])
+    assert rel < 0.03, rel
+
+
+def test_native_unet_through_nodes():
+    cfg = unet.mini_sdxl_config()
+    torch.manual_seed(1)
+    m = unet.UNetModel(**cfg).to(device="cuda:0", dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    pa.ParallelAnything().setup_parallel(m, _chain(["cuda:0"]))
+    inp = unet.example_inputs(cfg, 2, 256, 256, ctx_len=77, device="cuda:0", dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = m(inp["x"], inp["timesteps"], context=inp["context"], y=inp["y"])
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+    rel = (got.float() - want).abs().mean().item() / want.abs().mean().item()
+    pa.cleanup_parallel_model(m)
+    assert rel < 0.04, rel
+
+
+@pytest.mark.multigpu
+def test_multi_gpu_fused_dp_matches_single():
+    n = min(torch.cuda.device_count(), 4)
+    devs = [f"cuda:{i}" for i in range(n)]
+    rel, eng = _flux_case(devs, batch=2 * n + 1)
+    assert rel < 0.03, rel
+    assert any(r.get("fused") for r in eng.metrics.rows), "fused in-process path was not taken"
+
+
+@pytest.mark.multigpu
+def test_multi_gpu_weighted_split_and_generic_module():
+    class Toy(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l = nn.Linear(16, 16)
+
+        def forward(self, x, timesteps, context=None, **kw):
+            return torch.tanh(self.l(x)) + timesteps[:, None] + context.mean(1)
+    m = Toy().to("cuda:0").eval()
+    plain = copy.deepcopy(m)
+    pa.ParallelAnything().setup_parallel(m, _chain(["cuda:0", "cuda:1"], [70, 30]))
+    x, t, c = torch.randn(10, 16, device="cuda:0"), torch.rand(10, device="cuda:0"), torch.randn(10, 3, 16, device="cuda:0")
+    with torch.no_grad():
+        got, want = m(x, t, context=c), plain(x, t, context=c)
+    torch.cuda.synchronize()
+    assert torch.allclose(got, want, atol=1e-5)
+    assert m._parallel_engine.metrics.rows[-1]["sizes"] == [7, 3]
+    pa.cleanup_parallel_model(m)
