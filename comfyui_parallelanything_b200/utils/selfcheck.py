@@ -547,3 +547,57 @@ def vae_decoder_executor():
         got = ex.decode(z)
         want = oracle(z.float())
     return _cmp("vae_decoder_executor", got, want, 0.03)
+
+
+# ------------------------------------------------------------------------------ MXFP8
+@check
+def gemm_mxfp8():
+    """tcgen05 block-scaled fp8 GEMM vs (a) the exact product of the dequantised operands (tests the kernel)
+    and (b) the bf16-input fp32 reference (shows the quantisation error level)."""
+    B, M, K, N = 2, 320, 1024, 768
+    a, w, bias = _rand(B, M, K), _rand(N, K, scale=0.03), _rand(N)
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, sfb = ops.quantize_mxfp8(w)
+    out = torch.zeros(B, M, N, dtype=torch.bfloat16, device=_dev())
+    ops.gemm_fp8(aq, sfa, wq, sfb, "gelu", out=out, bias=bias)
+    ad, wd = ops.dequantize_mxfp8(aq, sfa), ops.dequantize_mxfp8(wq, sfb)[0]
+    exact = F.gelu(ad @ wd.t() + bias.float(), approximate="tanh")
+    r = _cmp("gemm_mxfp8", out, exact, 0.01)
+    full = F.gelu(a.float() @ w.float().t() + bias.float(), approximate="tanh")
+    r["vs_bf16_inputs_mean_rel"] = _cmp("q", out, full, 1.0)["mean_rel"]
+    r["quant_roundtrip_rel"] = ((ad - a.float()).abs().mean() / a.float().abs().mean()).item()
+    return r
+
+
+@check
+def gemm_mxfp8_flux_shape():
+    M, K, N = 4608, 3072, 9216
+    a, w = _rand(M, K), _rand(N, K, scale=0.02)
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, sfb = ops.quantize_mxfp8(w)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=_dev())
+    ops.gemm_fp8(aq, sfa, wq, sfb, "bias", out=out)
+    exact = ops.dequantize_mxfp8(aq, sfa)[0] @ ops.dequantize_mxfp8(wq, sfb)[0].t()
+    r = _cmp("gemm_mxfp8_flux_shape", out, exact, 0.01)
+    # throughput (device timed)
+    for _ in range(3):
+        ops.gemm_fp8(aq, sfa, wq, sfb, "bias", out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.gemm_fp8(aq, sfa, wq, sfb, "bias", out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    r["ms"], r["tflops"] = ms, 2.0 * M * N * K / ms / 1e9
+    a16, w16 = a, w
+    o16 = torch.empty_like(out)
+    for _ in range(3):
+        ops.gemm(a16, w16, "bias", out=o16)
+    e0.record()
+    for _ in range(10):
+        ops.gemm(a16, w16, "bias", out=o16)
+    e1.record()
+    torch.cuda.synchronize()
+    r["bf16_ms"] = e0.elapsed_time(e1) / 10
+    return r

@@ -64,6 +64,8 @@ static void parse_epilogue(const py::kwargs& kw, pa::GemmParams& p, bool check_s
 
 // gemm(A, W, mode, out=..., bias=..., residual=..., gate=..., q=,k=,v=,q_scale=,k_scale=,rope=,heads=,seq_off=,
 //      mlp_col_off=, qk_eps=, x_in=, x_out= | x_out_ptr=, xout_sample_off=, sigmas=, C=,Hl=,Wl=, force_bn=)
+static void parse_modes(int mode, const py::kwargs& kw, pa::GemmParams& p);
+
 static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
   TORCH_CHECK(A.is_cuda() && W.is_cuda(), "gemm: CUDA tensors required");
   TORCH_CHECK(A.scalar_type() == at::kBFloat16 && W.scalar_type() == at::kBFloat16, "gemm: bf16 required");
@@ -77,6 +79,46 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
   TORCH_CHECK(A.size(-1) == p.K, "gemm: K mismatch");
   p.mode = mode;
   parse_epilogue(kw, p, /*check_shape=*/true);
+  parse_modes(mode, kw, p);
+  int force_bn = has(kw, "force_bn") ? kw["force_bn"].cast<int>() : 0;
+  check(pa::gemm_bf16(A.data_ptr(), lda, abs_, W.data_ptr(), W.stride(0), p, force_bn, cur_stream()), "gemm_bf16");
+}
+
+// MXFP8: A_q / W_q are uint8 (e4m3 bit patterns) contiguous, sfa / sfb uint8 scale chunks (see gemm_mxfp8.cu)
+static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, py::kwargs kw) {
+  TORCH_CHECK(A.is_cuda() && A.is_contiguous() && W.is_contiguous() && A.element_size() == 1 && W.element_size() == 1,
+              "gemm_fp8: contiguous 1-byte operands required");
+  c10::cuda::CUDAGuard guard(A.device());
+  pa::GemmParams p{};
+  long long lda, abs_;
+  view3(A, p.batch, p.rows, lda, abs_);
+  p.N = (int)W.size(0);
+  p.K = (int)W.size(1);
+  TORCH_CHECK(A.size(-1) == p.K, "gemm_fp8: K mismatch");
+  p.mode = mode;
+  parse_epilogue(kw, p, /*check_shape=*/true);
+  parse_modes(mode, kw, p);
+  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, cur_stream()), "gemm_mxfp8");
+}
+
+// bf16 [B, rows, K] / [rows, K] view -> (e4m3 bytes [B, rows, K], scale chunks)
+static std::vector<Tensor> quantize_mxfp8(Tensor x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16, "quantize_mxfp8: bf16 input");
+  int b, rows;
+  long long ld, bs;
+  view3(x, b, rows, ld, bs);
+  const int K = (int)x.size(-1);
+  TORCH_CHECK(K % 128 == 0, "quantize_mxfp8: K must be a multiple of 128");
+  auto o8 = x.options().dtype(at::kByte);
+  Tensor q = x.dim() == 2 ? at::empty({rows, K}, o8) : at::empty({b, rows, K}, o8);
+  Tensor sf = at::zeros({(int64_t)b * ((rows + 127) / 128) * (K / 128) * 512}, o8);
+  check(pa::quantize_mxfp8_rows(x.data_ptr(), ld, bs, q.data_ptr(), sf.data_ptr(), b, rows, K, cur_stream()),
+        "quantize_mxfp8_rows");
+  return {q, sf};
+}
+
+static void parse_modes(int mode, const py::kwargs& kw, pa::GemmParams& p) {
   if (mode == pa::EPI_QKV_ROPE) {
     Tensor q = ten(kw, "q");
     TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && q.is_contiguous(), "q must be [B, H, L, 128] contiguous");
@@ -119,8 +161,6 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
   } else {
     TORCH_CHECK(p.out != nullptr || mode == pa::EPI_QKV_ROPE, "gemm: out= required");
   }
-  int force_bn = has(kw, "force_bn") ? kw["force_bn"].cast<int>() : 0;
-  check(pa::gemm_bf16(A.data_ptr(), lda, abs_, W.data_ptr(), W.stride(0), p, force_bn, cur_stream()), "gemm_bf16");
 }
 
 // conv(x[N,H,W,Cin], w[Cout, taps*Cin_pad], taps, stride, mode, out=[N, Ho*Wo, Cout], bias=, residual=, gate=)
@@ -331,6 +371,8 @@ static void wait_flags(Tensor flags, int first, int n, uint32_t value, long long
 PYBIND11_MODULE(_C, m) {
   m.doc() = "comfyui-parallelanything_b200 native library (sm_100a kernels + runtime)";
   m.def("gemm", &gemm, py::arg("A"), py::arg("W"), py::arg("mode"));
+  m.def("gemm_fp8", &gemm_fp8, py::arg("A"), py::arg("sfa"), py::arg("W"), py::arg("sfb"), py::arg("mode"));
+  m.def("quantize_mxfp8", &quantize_mxfp8);
   m.def("conv", &conv, py::arg("x"), py::arg("w"), py::arg("taps"), py::arg("stride"), py::arg("mode"));
   m.def("layernorm_modulate", &layernorm_modulate, py::arg("x"), py::arg("out"), py::arg("scale") = py::none(),
         py::arg("shift") = py::none(), py::arg("gamma") = py::none(), py::arg("beta") = py::none(),

@@ -20,6 +20,11 @@ int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int ta
 int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, GemmParams p,
               int force_bn, cudaStream_t st);
 
+// block-scaled FP8 (MXFP8) GEMM + quantiser (csrc/kernels/gemm_mxfp8.cu)
+int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
+                        cudaStream_t st);
+int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, cudaStream_t st);
+
 // out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
 int layernorm_modulate(const void* x, long long ldx, long long x_bstride, void* out, long long ldo,
                        long long o_bstride, const void* scale, const void* shift, long long mod_bstride,

@@ -1,0 +1,293 @@
+// Block-scaled FP8 GEMM (OCP MXFP8: e4m3 elements, one UE8M0 scale per 32 K-elements) on tcgen05:
+//   tcgen05.mma.kind::mxf8f6f4.block_scale, operands through 128B-swizzled TMA tiles (K-block = 128 fp8 = 128 B),
+//   scale factors staged global -> smem (cp.async.bulk) -> TMEM (tcgen05.cp 32x128b.warpx4), fp32 accumulators
+//   double-buffered in TMEM, the SAME fused epilogues as the bf16 GEMM (bias/GELU/gated residual/QKV+RoPE/...).
+//
+// Scale-factor storage ("chunk" layout, identical for A and B, produced by quantize_mxfp8_rows below):
+//   for every 128 rows x 128 K-elements one 512-byte chunk; inside it the scale of row r = m0 + 32*m1
+//   (m0 < 32, m1 < 4) and K-block kb < 4 sits at byte m0*16 + m1*4 + kb.  That is exactly the
+//   32-lane x 128-bit image tcgen05.cp expects: lane m0, 32-bit column m1, byte kb (selected per MMA through
+//   the instruction descriptor's sf_id fields).
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+#include "../common/host.h"
+#include "gemm_tcgen05.cuh"
+
+namespace pa {
+
+template <int BN>
+struct Mx8Cfg {
+  static constexpr int BM = 128, BK = 128;                       // BK in elements == bytes
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BM * BK, B_BYTES = BN * BK;
+  static constexpr uint32_t SFA_BYTES = 512, SFB_BYTES = 512 * (BN / 128);
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
+  static constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t ACC_COLS = 2 * BN;                   // double-buffered accumulators
+  static constexpr uint32_t SF_COL = ACC_COLS;                   // SFA: 4 columns, SFB: 4 * BN/128 columns
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_STRIDE + 256 + 1024;
+  static_assert(ACC_COLS + 4 + 4 * (BN / 128) <= 512, "TMEM budget");
+};
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ptx::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+// smem descriptor of a 32-row x 16-byte scale-factor image (no swizzle; 8-row atoms 128 B apart)
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 32;   // SBO
+  d |= static_cast<uint64_t>(1) << 46;          // descriptor version (sm_100)
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const uint8_t* __restrict__ sfa, const uint8_t* __restrict__ sfb, const GemmParams p) {
+  using Cfg = Mx8Cfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_STRIDE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_per_batch = (p.rows + BM - 1) / BM;
+  const int num_m = m_per_batch * p.batch;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;                      // K % 128 == 0 (checked on the host)
+  constexpr int GROUP_M = 8;
+  auto decode = [&](int t, int& mt, int& nt) {
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first = g * GROUP_M;
+    const int gsz = min(num_m - first, GROUP_M);
+    const int r = t - g * per_group;
+    mt = first + r % gsz;
+    nt = r / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int mt, nt;
+        decode(t, mt, nt);
+        const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
+        const uint8_t* sfa_t = sfa + static_cast<long long>(mt) * num_k * 512;
+        const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * (BN / 128) * num_k * 512;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + stage * Cfg::STAGE_STRIDE;
+          ptx::tma_load_3d(sa, &tmA, &full[stage], kb * BK, mrow, b);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
+          bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES, sfa_t + static_cast<long long>(kb) * 512, 512, &full[stage]);
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j)
+            bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES + 512 + j * 512,
+                         sfb_t + (static_cast<long long>(j) * num_k + kb) * 512, 512, &full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const uint32_t sfa_t = tmem_base + Cfg::SF_COL, sfb_t = tmem_base + Cfg::SF_COL + 4;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_STRIDE);
+          // scale factors of this K-block: smem -> TMEM (ordered with the MMAs in the tensor-core pipe)
+          ptx::tmem_cp_32x128b_warpx4(sfa_t, make_sf_desc(sa + Cfg::A_BYTES + Cfg::B_BYTES));
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j)
+            ptx::tmem_cp_32x128b_warpx4(sfb_t + 4 * j, make_sf_desc(sa + Cfg::A_BYTES + Cfg::B_BYTES + 512 + j * 512));
+          const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {        // 4 x (K = 32 fp8 = 32 bytes); sf_id = K-block inside the chunk
+            const uint32_t idesc = ptx::make_idesc_mxf8(BM, BN, 0, 0, k, k);
+            ptx::mma_mxf8_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, sfa_t, sfb_t, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty[stage]);
+          if (kb == num_k - 1) ptx::tc_commit(&tfull[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q4 = warp & 3;
+    const int r_in_tile = q4 * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int mt, nt;
+      decode(t, mt, nt);
+      const int b = mt / m_per_batch;
+      const int row = (mt - b * m_per_batch) * BM + r_in_tile;
+      const int acc = it & 1;
+      ptx::mbar_wait(&tfull[acc], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
+      epilogue_tile<BN>(p, taddr, b, row, row < p.rows, nt * BN);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ quantiser
+// bf16 [batch, rows, K] (strided) -> e4m3 [batch, rows, K] + UE8M0 scales in the chunk layout.
+// One thread per 32-element block.  scale = 2^ceil(log2(amax / 448)); rows >= `rows` of the last 128-row
+// tile keep scale byte 0 (the caller zero-initialises the SF buffer) and are zero-filled by TMA.
+__global__ void quantize_mxfp8_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long x_bs,
+                                      uint8_t* __restrict__ q, uint8_t* __restrict__ sf, int batch, int rows, int K) {
+  const int kblocks = K >> 5;
+  const long long total = static_cast<long long>(batch) * rows * kblocks;
+  const int m_tiles = (rows + 127) >> 7, kchunks = K >> 7;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kb = static_cast<int>(i % kblocks);
+    const long long rr = i / kblocks;
+    const int r = static_cast<int>(rr % rows);
+    const int b = static_cast<int>(rr / rows);
+    const uint4* src = reinterpret_cast<const uint4*>(x + b * x_bs + static_cast<long long>(r) * ldx + kb * 32);
+    float v[32];
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 u = __ldg(src + j);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        v[j * 8 + 2 * e] = f.x;
+        v[j * 8 + 2 * e + 1] = f.y;
+        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+      }
+    }
+    int e = -127;
+    if (amax > 0.f) {
+      e = static_cast<int>(ceilf(log2f(amax * (1.0f / 448.0f))));
+      e = max(-127, min(127, e));
+    }
+    const float inv = exp2f(static_cast<float>(-e));
+    uint32_t packed[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j] * inv, v[4 * j + 1] * inv),
+                                                               __NV_SATFINITE, __NV_E4M3);
+      const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j + 2] * inv, v[4 * j + 3] * inv),
+                                                               __NV_SATFINITE, __NV_E4M3);
+      packed[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(q + (static_cast<long long>(b) * rows + r) * K + kb * 32);
+    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    const int mt = r >> 7, r128 = r & 127;
+    const long long chunk = (static_cast<long long>(b) * m_tiles + mt) * kchunks + (kb >> 2);
+    sf[chunk * 512 + (r128 & 31) * 16 + (r128 >> 5) * 4 + (kb & 3)] = static_cast<uint8_t>(e + 127);
+  }
+}
+
+int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
+                        cudaStream_t st) {
+  if (K % 128 || ldx % 8 || x_bs % 8) return -1;
+  const long long total = static_cast<long long>(batch) * rows * (K / 32);
+  const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+  quantize_mxfp8_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_bs,
+                                                static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), batch, rows, K);
+  return (int)cudaGetLastError();
+}
+
+template <int BN>
+static int launch_mx8(const CUtensorMap& ta, const CUtensorMap& tb, const void* sfa, const void* sfb,
+                      const GemmParams& p, int tiles, cudaStream_t st) {
+  using Cfg = Mx8Cfg<BN>;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_mxfp8_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, static_cast<const uint8_t*>(sfa),
+                                                            static_cast<const uint8_t*>(sfb), p);
+  return (int)cudaGetLastError();
+}
+
+// A: e4m3 [batch, rows, K] contiguous, W: e4m3 [N, K] contiguous (N % 128 == 0), scales in chunk layout.
+int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, cudaStream_t st) {
+  if (p.K % 128 || p.N % 128) return -10;
+  constexpr int BN = 128;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
+    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint32_t box[3] = {128, 128, 1};
+    if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {1, (uint64_t)p.K};
+    uint32_t box[2] = {128, (uint32_t)BN};
+    if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
+  }
+  const int tiles = ((p.rows + 127) / 128) * p.batch * (p.N / BN);
+  return launch_mx8<BN>(ta, tb, sfa, sfb, p, tiles, st);
+}
+
+}  // namespace pa
