@@ -168,7 +168,7 @@ def run_ours(args) -> int:
     torch.manual_seed(1234)                          # identical random-init weights on every rank
     with torch.device(dev):
         model = flux.Flux(params, dtype=torch.bfloat16)
-    ex = FluxExecutor(model, dev)
+    ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"))
     del model
     torch.cuda.empty_cache()
 
@@ -233,7 +233,8 @@ def run_ours(args) -> int:
         emit({"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
               "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
               "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / 0.0775, 2),
-              "dtype": "bf16", "data": "synthetic latents/conditioning of the named shape, random-init weights",
+              "dtype": "bf16" if args.dtype == "bf16" else "fp8 (MXFP8 block-scaled GEMMs; attention/norms bf16)",
+              "data": "synthetic latents/conditioning of the named shape, random-init weights",
               "impl": "ours", "clocks": clocks,
               "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
@@ -355,6 +356,8 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--backend", default=os.environ.get("PA_BACKEND", "fused"), choices=["fused", "nccl"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8); default bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

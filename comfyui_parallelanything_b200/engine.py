@@ -205,7 +205,7 @@ class ParallelEngine:
         faults.check_setup(name, index)
         log.info("Building native sm_100a %s executor on %s (free VRAM %.0f MiB)",
                  getattr(self.target, "pa_family", "?"), name, memory.get_free_vram(name))
-        return build(self.target, dev, cuda_graphs=self.config.cuda_graphs)
+        return build(self.target, dev, cuda_graphs=self.config.cuda_graphs, fp8=self.config.fp8)
 
     # ------------------------------------------------------------------ forward
     def _replica_call(self, replica: nn.Module, *a, **k):

@@ -35,7 +35,7 @@ class FluxExecutor(nn.Module):
     pa_family = "flux"
     pa_native = True
 
-    def __init__(self, model: "flux_model.Flux", device, cuda_graphs: bool = False):
+    def __init__(self, model: "flux_model.Flux", device, cuda_graphs: bool = False, fp8: bool = False):
         super().__init__()
         ops.require()
         self.device = torch.device(device)
@@ -47,6 +47,10 @@ class FluxExecutor(nn.Module):
             raise ValueError("FluxExecutor is specialised for 2x2 patches")
         self.mlp = int(p.hidden_size * p.mlp_ratio)
         self.cuda_graphs = cuda_graphs
+        # fp8=True: the block GEMMs (qkv / proj / mlp / linear1 / linear2 = 99.9 % of the FLOPs) run as MXFP8
+        # block-scaled tcgen05 GEMMs (weights quantised once here, activations per GEMM); embedders,
+        # modulation and the final layer stay bf16.
+        self.fp8 = bool(fp8)
         # the fused scatter/patch-embed kernel is specialised for 16 latent channels x (2x2) patches
         self.fused_embed = (p.in_channels == 64)
         d = self.device
@@ -99,6 +103,17 @@ class FluxExecutor(nn.Module):
         W["mod.b"] = torch.cat([_bf16(m.bias, d) for m in mods], dim=0).contiguous()
         lin("final", model.final_layer.linear)
         self.W = W
+        if self.fp8:
+            big = [k[:-2] for k in list(W) if k.endswith(".w") and (k.startswith("d") or k.startswith("s"))
+                   and k.split(".")[-2] in ("qkv", "proj", "mlp0", "mlp2", "l1", "l2")]
+            for name in big:
+                w = W.pop(name + ".w")
+                if w.shape[0] % 128 or w.shape[1] % 128:
+                    W[name + ".w"] = w
+                    continue
+                W[name + ".q"], W[name + ".sf"] = ops.quantize_mxfp8(w)
+                del w
+            torch.cuda.empty_cache()
         self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
         self._ws: Dict[Tuple, dict] = {}
         self._graphs: Dict[Tuple, Tuple] = {}
@@ -146,6 +161,17 @@ class FluxExecutor(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ schedule
+    def _lin(self, a, name: str, mode: str, **kw) -> int:
+        """One block Linear: bf16 tcgen05 GEMM, or (fp8) quantise the activation + block-scaled fp8 GEMM.
+        Returns the number of kernel launches."""
+        W = self.W
+        if name + ".q" in W:
+            aq, sfa = ops.quantize_mxfp8(a)
+            ops.gemm_fp8(aq, sfa, W[name + ".q"], W[name + ".sf"], mode, bias=W[name + ".b"], **kw)
+            return 3
+        ops.gemm(a, W[name + ".w"], mode, bias=W[name + ".b"], **kw)
+        return 1
+
     def _mod(self, ws, key, idx):
         off = self.mod_off[key] + idx * self.hid
         return ws["MOD"][:, off:off + self.hid]
@@ -195,28 +221,26 @@ class FluxExecutor(nn.Module):
             for s, xs, xms, seq_off in (("img", Xi, XMi, Lt), ("txt", Xt, XMt, 0)):
                 k = ("d", i, s)
                 ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
-                ops.gemm(xms, W[f"d{i}.{s}.qkv.w"], "qkv_rope", bias=W[f"d{i}.{s}.qkv.b"], q=Q, k=K, v=V,
-                         q_scale=W[f"d{i}.{s}.qs"], k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
+                n += self._lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
+                               k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
             ops.attention(Q, K, V, out=ATT)
-            n += 5
+            n += 3
             for s, xs, xms, a, mh in (("img", Xi, XMi, ATT[:, Lt:], MH[:, Lt:]), ("txt", Xt, XMt, ATT[:, :Lt], MH[:, :Lt])):
                 k = ("d", i, s)
-                ops.gemm(a, W[f"d{i}.{s}.proj.w"], "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2),
-                         bias=W[f"d{i}.{s}.proj.b"])
+                n += self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
                 ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 4), shift=self._mod(ws, k, 3))
-                ops.gemm(xms, W[f"d{i}.{s}.mlp0.w"], "gelu", out=mh, bias=W[f"d{i}.{s}.mlp0.b"])
-                ops.gemm(mh, W[f"d{i}.{s}.mlp2.w"], "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5),
-                         bias=W[f"d{i}.{s}.mlp2.b"])
-                n += 4
+                n += self._lin(xms, f"d{i}.{s}.mlp0", "gelu", out=mh)
+                n += self._lin(mh, f"d{i}.{s}.mlp2", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5))
+                n += 1
         # ---- single-stream blocks
         for i in range(self.n_single):
             k = ("s", i)
             ops.layernorm_modulate(X, XM, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
-            ops.gemm(XM, W[f"s{i}.l1.w"], "qkv_rope", bias=W[f"s{i}.l1.b"], q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"],
-                     k_scale=W[f"s{i}.ks"], rope=ROPE, seq_off=0, out=CAT, mlp_col_off=hid)
+            n += self._lin(XM, f"s{i}.l1", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"], k_scale=W[f"s{i}.ks"],
+                           rope=ROPE, seq_off=0, out=CAT, mlp_col_off=hid)
             ops.attention(Q, K, V, out=ATT)
-            ops.gemm(CAT, W[f"s{i}.l2.w"], "gate_res", out=X, residual=X, gate=self._mod(ws, k, 2), bias=W[f"s{i}.l2.b"])
-            n += 4
+            n += self._lin(CAT, f"s{i}.l2", "gate_res", out=X, residual=X, gate=self._mod(ws, k, 2))
+            n += 2
         # ---- final layer: AdaLN + Linear + unpatchify (+ Euler update, + peer store)
         k = ("final",)
         ops.layernorm_modulate(Xi, XMi, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))

@@ -169,7 +169,7 @@ class UNetExecutor(nn.Module):
     pa_family = "unet"
     pa_native = True
 
-    def __init__(self, model: "unet_model.UNetModel", device, cuda_graphs: bool = False):
+    def __init__(self, model: "unet_model.UNetModel", device, cuda_graphs: bool = False, fp8: bool = False):
         super().__init__()
         ops.require()
         d = self.device = torch.device(device)

@@ -72,7 +72,7 @@ class VAEDecoderExecutor(nn.Module):
     pa_family = "vae"
     pa_native = True
 
-    def __init__(self, model: "vae_model.VAEDecoder", device, cuda_graphs: bool = False):
+    def __init__(self, model: "vae_model.VAEDecoder", device, cuda_graphs: bool = False, fp8: bool = False):
         super().__init__()
         ops.require()
         d = self.device = torch.device(device)

@@ -33,7 +33,7 @@ class WanExecutor(nn.Module):
     pa_family = "wan"
     pa_native = True
 
-    def __init__(self, model: "wan_model.WanModel", device, cuda_graphs: bool = False):
+    def __init__(self, model: "wan_model.WanModel", device, cuda_graphs: bool = False, fp8: bool = False):
         super().__init__()
         ops.require()
         d = self.device = torch.device(device)

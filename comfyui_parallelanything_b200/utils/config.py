@@ -14,6 +14,7 @@ Environment variables (all optional):
 ``PA_BACKEND``         ``auto`` | ``fused`` (sm_100a kernels + in-kernel P2P) |
                        ``nccl`` (baseline collectives) | ``torch`` (threads)
 ``PA_CUDA_GRAPHS``     ``1``/``0`` capture replica forward in CUDA graphs
+``PA_FP8``             ``1``: block-scaled fp8 (MXFP8) GEMMs in the native DiT executors
 ``PA_FAULT``           fault injection, e.g. ``oom:cuda:1@setup``,
                        ``raise:1@step3``, ``oom:1@step2`` (see utils/faults.py)
 ``PA_FLAG_TIMEOUT_MS`` watchdog for in-kernel flag waits (default 20000)
@@ -44,6 +45,7 @@ class EngineConfig:
     backend: str = field(default_factory=lambda: os.environ.get("PA_BACKEND", "auto"))
     cuda_graphs: bool = field(default_factory=lambda: _env_bool("PA_CUDA_GRAPHS", True))
     flag_timeout_ms: int = field(default_factory=lambda: int(os.environ.get("PA_FLAG_TIMEOUT_MS", "20000")))
+    fp8: bool = field(default_factory=lambda: _env_bool("PA_FP8", False))   # MXFP8 block GEMMs in native executors
     cache_conditioning: bool = True       # do not re-send constant context every step
     pair_cfg: bool = False                # keep cond/uncond of one sample on one rank
 

@@ -601,3 +601,27 @@ def gemm_mxfp8_flux_shape():
     torch.cuda.synchronize()
     r["bf16_ms"] = e0.elapsed_time(e1) / 10
     return r
+
+
+@check
+def flux_executor_fp8():
+    """FLUX executor with MXFP8 block GEMMs vs the fp32 oracle (loose tolerance: e4m3 has 3 mantissa bits)."""
+    from ..exec.flux_exec import FluxExecutor
+    from ..models import flux
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=512,
+                        mlp_ratio=4.0, num_heads=4, depth=2, depth_single_blocks=2)
+    torch.manual_seed(1)
+    m = flux.Flux(p).to(device=_dev(), dtype=torch.bfloat16).eval()
+    ex8 = FluxExecutor(m, _dev(), fp8=True)
+    ex16 = FluxExecutor(m, _dev())
+    oracle = flux.Flux(p).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    inp = flux.example_inputs(p, 2, 256, 256, txt_len=128, device=_dev(), dtype=torch.bfloat16, seed=3)
+    with torch.no_grad():
+        got8, got16 = ex8(**inp), ex16(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+    r = _cmp("flux_executor_fp8", got8, want, 0.12)
+    r["bf16_mean_rel"] = _cmp("bf16", got16, want, 1.0)["mean_rel"]
+    r["n_fp8_weights"] = sum(1 for k in ex8.W if k.endswith(".q"))
+    r["ok"] = r["ok"] and r["n_fp8_weights"] > 0
+    return r
