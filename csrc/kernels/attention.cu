@@ -5,7 +5,10 @@
 //   warp 0   TMA producer: Q once, then K_j / V_j tiles (128 keys) through 2-stage rings
 //   warp 1   tcgen05.mma issuer:  S_j = Q K_j^T  (TMEM, double buffered)  and  O_j = P_j V_j (TMEM, double buffered)
 //   warp 2   TMEM allocator
-//   warps 4-7  softmax: thread == query row.  S_j is read from TMEM once (128 registers), row max with
+//   warps 4-11 softmax: TWO warpgroups split the 128 key columns of every S_j tile (two threads per query row,
+//            row max exchanged through shared memory), so each scheduler has two softmax warps to overlap
+//            the TMEM-load / MUFU / barrier latencies of one with the math of the other.
+//            S_j is read from TMEM once (64 registers per thread), row max with
 //            3-input FMNMX, exp2 with packed FFMA2/FADD2, P_j written to shared memory as a 128B-swizzled
 //            K-major A operand.  O accumulates IN TMEM across all KV tiles (tcgen05.mma accumulate);
 //            it is only rescaled (tcgen05.ld -> mul -> tcgen05.st) when the running row max grows by
@@ -30,7 +33,8 @@ struct AttnCfg {
   static constexpr uint32_t OFF_V = OFF_K + 2 * QKV_TILE;          // 2 stages
   static constexpr uint32_t OFF_P = OFF_V + 2 * QKV_TILE;          // 2 buffers
   static constexpr uint32_t OFF_BAR = OFF_P + 2 * P_TILE;
-  static constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t OFF_XCHG = OFF_BAR + 256;              // float[2 (tile parity)][2 (half)][128 rows]
+  static constexpr uint32_t SMEM_BYTES = OFF_XCHG + 2048 + 768;    // D=128: exactly the 227 KB per-CTA limit
   static constexpr uint32_t TMEM_COLS = 512;                       // S0 @0, S1 @128, O @256 (D columns)
 };
 
@@ -94,7 +98,7 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, flo
 }
 
 template <int D>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
                  long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
@@ -103,7 +107,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES, TILE_BYTES = Cfg::QKV_TILE, P_TILE = Cfg::P_TILE;
   constexpr uint32_t OFF_Q = Cfg::OFF_Q, OFF_K = Cfg::OFF_K, OFF_V = Cfg::OFF_V, OFF_P = Cfg::OFF_P,
                      OFF_BAR = Cfg::OFF_BAR, TMEM_COLS = Cfg::TMEM_COLS;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars;            // 1
@@ -137,12 +141,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&s_empty[i], 4);
+      ptx::mbar_init(&s_empty[i], 8);
       ptx::mbar_init(&o_full[i], 1);
       ptx::mbar_init(&o_empty[i], 4);      // (unused since O accumulates in TMEM)
     }
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_full[i], 8);
       ptx::mbar_init(&p_empty[i], 1);
     }
     ptx::fence_barrier_init();
@@ -222,11 +226,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp >= 4) {
     const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;                  // 0: key columns 0..63 of each tile, 1: columns 64..127
     const int r = q4 * 32 + lane;                      // query row inside the tile
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
-    const uint32_t o_addr = lane_addr + 256;
+    constexpr int OH = D / 2;                          // output columns owned by this thread
+    const uint32_t o_addr = lane_addr + 256 + half * OH;
     float m_used = -INFINITY, l = 0.f;
-    uint8_t* p_row0 = smem + OFF_P + r * 128;
+    uint8_t* p_row0 = smem + OFF_P + half * SLICE_BYTES + r * 128;
+    float* xchg = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);
     const int sw = r & 7;
     const unsigned long long sl2 = pack2(scale_log2, scale_log2);
 
@@ -234,48 +241,47 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int s = j & 1;
       ptx::mbar_wait(&s_full[s], (j >> 1) & 1);
       ptx::tc_fence_after();
-      uint32_t sv[128];
+      uint32_t sv[64];
       {
         uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
         uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        uint32_t(&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
-        uint32_t(&c3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128, c0);
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 32, c1);
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 64, c2);
-        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + 96, c3);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + half * 64, c0);
+        ptx::tmem_ld_32x32b_x32(lane_addr + s * 128 + half * 64 + 32, c1);
         ptx::tmem_ld_wait();
       }
-      // S_j is in registers: hand the TMEM buffer back so QK^T of tile j+2 can start
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&s_empty[s]);
+      if (lane == 0) ptx::mbar_arrive(&s_empty[s]);      // S_j is in registers: QK^T of tile j+2 may start
 
-      const int kv_left = Lk - j * BN;                  // < 128 only on a ragged last tile
-      if (kv_left < BN) {
+      const int kv_left = Lk - j * BN - half * 64;       // valid columns of this half (ragged last tile only)
+      if (kv_left < 64) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= kv_left) sv[i] = 0xff800000u;        // -inf
+        for (int i = 0; i < 64; ++i)
+          if (i >= kv_left) sv[i] = 0xff800000u;         // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
+      for (int i = 0; i < 64; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
         mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
       }
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_used));
+      const float mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xb = xchg + s * 256;
+      xb[half * 128 + r] = mine;
+      ptx::named_bar_sync(1, 256);                       // the two column halves of every row exchange maxima
+      const float m_new = fmaxf(fmaxf(mine, xb[(half ^ 1) * 128 + r]), m_used);
       const bool need = (m_new - m_used) * scale_log2 > 8.0f;      // always true on the first tile
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2f((m_used - m_new) * scale_log2) : 1.0f;
         if (need) m_used = m_new;
         l *= alpha;
-        if (j > 0) {                                    // O currently holds tiles 0..j-1
+        if (j > 0) {                                     // O currently holds tiles 0..j-1
           ptx::mbar_wait(&o_full[0], (j - 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < OH / 32; ++c) {
             uint32_t t[32];
             ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
             ptx::tmem_ld_wait();
@@ -289,11 +295,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
-      ptx::mbar_wait(&p_empty[s], ((j >> 1) & 1) ^ 1);  // PV of tile j-2 has consumed this P buffer
+      ptx::mbar_wait(&p_empty[s], ((j >> 1) & 1) ^ 1);   // PV of tile j-2 has consumed this P buffer
       uint8_t* p_row = p_row0 + s * P_TILE;
       unsigned long long sum2 = pack2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -313,12 +319,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        // 32 keys = 64 bytes = four 16-byte chunks of this row inside slice (c / 2)
-        uint8_t* base = p_row + (c >> 1) * SLICE_BYTES;
+        // 32 keys = 64 bytes = four 16-byte chunks of this row inside this half's 64-key slice
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = ((c & 1) * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          const int chunk = (c * 4 + q) ^ sw;
+          *reinterpret_cast<uint4*>(p_row + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
       }
       float s0, s1;
@@ -329,15 +334,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(&p_full[s]);
     }
 
-    // ---- epilogue: O / l -> bf16
+    // ---- epilogue: combine the two partial row sums, O / l -> bf16 (each thread writes its D/2 columns)
+    float* xl = xchg + (n_kv & 1) * 256;
+    xl[half * 128 + r] = l;
+    ptx::named_bar_sync(1, 256);
+    l += xl[(half ^ 1) * 128 + r];
     ptx::mbar_wait(&o_full[0], (n_kv - 1) & 1);
     ptx::tc_fence_after();
     const int q_row = q0 + r;
     const float inv = 1.0f / l;
     const int b = bh / H, h = bh - b * H;
-    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D + half * OH;
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OH / 32; ++c) {
       uint32_t t[32];
       ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
       ptx::tmem_ld_wait();
@@ -393,7 +402,7 @@ static int launch_attention(const void* q, const void* k, const void* v, void* o
   }
   dim3 grid((Lq + Cfg::BM - 1) / Cfg::BM, B * H);
   const float scale_log2 = scale * 1.4426950408889634f;
-  attention_kernel<D><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride,
+  attention_kernel<D><<<grid, 384, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride,
                                                          H, Lq, Lk, scale_log2);
   return (int)cudaGetLastError();
 }
