@@ -168,7 +168,7 @@ def run_ours(args) -> int:
     torch.manual_seed(1234)                          # identical random-init weights on every rank
     with torch.device(dev):
         model = flux.Flux(params, dtype=torch.bfloat16)
-    ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"))
+    ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
     del model
     torch.cuda.empty_cache()
 
@@ -356,6 +356,7 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--backend", default=os.environ.get("PA_BACKEND", "fused"), choices=["fused", "nccl"])
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
                     help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8); default bf16")
     args = ap.parse_args()

@@ -310,9 +310,35 @@ class FluxExecutor(nn.Module):
             ws = self.workspace(x.shape[0], x.shape[2], x.shape[3], context.shape[1])
             if out is None and out_ptr is None:
                 out = ws["OUT"]
-            self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, y, guidance, out,
-                      x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
-                      g_ptr=g_src_ptr, x_copy=x if (x_src_ptr is not None and self.fused_embed) else None)
+
+            def body():
+                self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, y, guidance,
+                          out, x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
+                          g_ptr=g_src_ptr, x_copy=x if (x_src_ptr is not None and self.fused_embed) else None)
+
+            if not self.cuda_graphs:
+                body()
+                return out
+            # The whole step (~410 launches) is replayed as ONE CUDA graph once the same buffers have been
+            # seen twice: every pointer the kernels use (inputs, peer mappings, output) is baked into the graph,
+            # so it is keyed on all of them and any change falls back to eager launches.
+            key = (tuple(x.shape), x.data_ptr(), timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
+                   y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, sigmas.data_ptr(),
+                   out.data_ptr() if out is not None else 0, out_ptr or 0, out_sample_off, x_src_ptr or 0,
+                   t_src_ptr or 0, g_src_ptr or 0)
+            g = self._graphs.get(key)
+            if g is None:
+                body()
+                self._graphs[key] = "seen"
+            elif g == "seen":
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                self._graphs[key] = graph
+                graph.replay()
+            else:
+                g.replay()
             return out
 
 
