@@ -175,6 +175,7 @@ class UNetExecutor(nn.Module):
         d = self.device = torch.device(device)
         self.mc, self.in_ch, self.out_ch = model.model_channels, model.in_channels, model.out_channels
         self.adm = model.adm_in_channels
+        self.ctx_dim = model.context_dim
         self.t1, self.t2 = _Lin(model.time_embed[0], d), _Lin(model.time_embed[2], d)
         if self.adm is not None:
             self.l1, self.l2 = _Lin(model.label_emb[0][0], d), _Lin(model.label_emb[0][2], d)

@@ -100,20 +100,15 @@ class SpmdFluxEngine:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.backend = backend
-        p = executor.params
         self.B, self.H, self.W, self.Lt = global_batch, height // 8, width // 8, txt_len
-        self.C = p.in_channels // 4
+        self.C = self._latent_channels()
         w = list(weights) if weights is not None else [1.0 / self.world] * self.world
         self.sizes = chain_mod.split_sizes(global_batch, chain_mod.normalize_weights(w), split_mode)
         self.offs = chain_mod.offsets(self.sizes)
         self.n_local, self.off_local = self.sizes[self.rank], self.offs[self.rank]
         B = global_batch
         bf = torch.bfloat16
-        self.spec = {      # name -> (shape, dtype) of rank 0's staging area
-            "x": ((B, self.C, self.H, self.W), bf), "t": ((B,), bf), "ctx": ((B, txt_len, p.context_in_dim), bf),
-            "y": ((B, p.vec_in_dim), bf), "g": ((B,), bf), "sig": ((B, 2), torch.float32),
-            "out": ((B, self.C, self.H, self.W), bf),
-        }
+        self.spec = self._make_spec(B)      # name -> (shape, dtype) of rank 0's staging area
         total = 4096
         for shape, dt in self.spec.values():
             n = 1
@@ -138,13 +133,40 @@ class SpmdFluxEngine:
         self.epoch = 0
         # local shard buffers (inputs are pulled from rank 0 into these)
         n = max(self.n_local, 1)
-        e = lambda *s, dt=bf: torch.empty(*s, dtype=dt, device=self.dev)  # noqa: E731
-        self.loc = dict(x=e(n, self.C, self.H, self.W), t=e(n), ctx=e(n, txt_len, p.context_in_dim),
-                        y=e(n, p.vec_in_dim), g=e(n), sig=e(n, 2, dt=torch.float32))
+        self.loc = {k: torch.empty((n,) + tuple(shape[1:]), dtype=dt, device=self.dev)
+                    for k, (shape, dt) in self.spec.items() if k != "out"}
+        self.input_names = tuple(k for k in self.spec if k != "out")
         self.comm_launches = 0
         self.tma_peer = os.environ.get("PA_TMA_PEER", "1") != "0"
         log.info("SPMD rank %d/%d: samples [%d, %d) of %d, backend=%s", self.rank, self.world, self.off_local,
                  self.off_local + self.n_local, B, backend)
+
+    # -------------------------------------------------------------- family hooks (FLUX defaults)
+    def _latent_channels(self) -> int:
+        return self.ex.params.in_channels // 4
+
+    def _make_spec(self, B: int) -> dict:
+        p, bf = self.ex.params, torch.bfloat16
+        return {"x": ((B, self.C, self.H, self.W), bf), "t": ((B,), bf), "ctx": ((B, self.Lt, p.context_in_dim), bf),
+                "y": ((B, p.vec_in_dim), bf), "g": ((B,), bf), "sig": ((B, 2), torch.float32),
+                "out": ((B, self.C, self.H, self.W), bf)}
+
+    def _launch(self, loc: dict, fused: bool) -> None:
+        """Run the replica on this rank's shard.  ``fused``: pull x/t/g inside the first kernel from rank 0 and
+        store the result rows into rank 0's output buffer from the last kernel's epilogue."""
+        if fused:
+            x_bytes = self.C * self.H * self.W * 2
+            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"],
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                 x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2),
+                                 g_src_ptr=self._src("g", 2))
+            return None
+        return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"])
+
+    #: inputs that the replica's GEMMs may read straight from rank 0's HBM through TMA descriptors
+    tma_peer_inputs = ("ctx", "y")
+    #: inputs the first kernel pulls itself (never copied separately on the fused path)
+    kernel_pulled_inputs = ("x", "t", "g")
 
     # -------------------------------------------------------------- helpers
     def _src(self, name: str, row_bytes: int) -> int:
@@ -167,11 +189,12 @@ class SpmdFluxEngine:
         self.heap.C.memcpy_async(dst.data_ptr(), self._src(name, row_bytes), row_bytes * self.n_local, 4,
                                  torch.cuda.current_stream().cuda_stream)
 
-    def stage_inputs(self, x, t, ctx, y, g, sig) -> int:
+    def stage_inputs(self, *tensors, **named) -> int:
         """rank 0: copy this step's inputs (pinned host or device tensors) into the symmetric
-        staging area.  Returns the number of bytes copied."""
+        staging area (positional order = ``self.input_names``).  Returns the number of bytes copied."""
         nbytes = 0
-        for name, src in (("x", x), ("t", t), ("ctx", ctx), ("y", y), ("g", g), ("sig", sig)):
+        items = list(zip(self.input_names, tensors)) + list(named.items())
+        for name, src in items:
             self.buf[name].copy_(src, non_blocking=True)
             nbytes += self.buf[name].numel() * self.buf[name].element_size()
         return nbytes
@@ -193,28 +216,22 @@ class SpmdFluxEngine:
         n += 1
         if self.n_local > 0:
             if self.rank == 0:
-                loc = {k: self.buf[k][self.off_local:self.off_local + self.n_local] for k in ("x", "t", "ctx", "y", "g", "sig")}
+                loc = {k: self.buf[k][self.off_local:self.off_local + self.n_local] for k in self.input_names}
             else:
                 loc = {k: v[:self.n_local] for k, v in self.loc.items()}
-                if self.tma_peer:
-                    # conditioning / pooled vector are consumed by TMA directly from the lead's HBM
-                    # (A operand of txt_in / vector_in over NVLink); only the 8-byte sigmas are copied
-                    self._pull("sig")
-                    n += 1
-                    loc["ctx"] = self._peer_view("ctx")
-                    loc["y"] = self._peer_view("y")
-                else:
-                    for name in ("ctx", "y", "sig"):
+                for name in self.input_names:
+                    if name in self.kernel_pulled_inputs:
+                        continue
+                    if self.tma_peer and name in self.tma_peer_inputs:
+                        # consumed by TMA directly from the lead's HBM (A operand of a GEMM over NVLink)
+                        loc[name] = self._peer_view(name)
+                    else:
                         self._pull(name)
                         n += 1
-            x_bytes = self.C * self.H * self.W * 2
-            # fused scatter: the patchify/embed kernel loads this rank's latent shard directly from
-            # rank 0's buffer over NVLink; fused gather: the last GEMM epilogue stores x_{t-1} rows at
-            # their final offset in rank 0's output buffer.
-            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"],
-                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
-                                 x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2),
-                                 g_src_ptr=self._src("g", 2))
+            # fused scatter: the first kernel loads this rank's latent shard directly from rank 0's buffer over
+            # NVLink; fused gather: the last kernel stores x_{t-1} rows at their final offset in rank 0's
+            # output buffer.
+            self._launch(loc, fused=True)
             n += self.ex.launches_per_step
         C.signal_flags(self.lead_flag_table, 1, self.FLAG_DONE0 + self.rank, e)
         n += 1
@@ -228,7 +245,7 @@ class SpmdFluxEngine:
         """Baseline: NCCL point-to-point scatter/gather around the same executor (what "just call
         the library" costs; not the product path)."""
         loc = {}
-        for k in ("x", "t", "ctx", "y", "g", "sig"):
+        for k in self.input_names:
             if self.rank == 0:
                 for r in range(1, self.world):
                     if self.sizes[r]:
@@ -240,7 +257,7 @@ class SpmdFluxEngine:
                     dist.recv(loc[k], src=0)
         out = None
         if self.n_local:
-            out = self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["y"], loc["g"], loc["sig"])
+            out = self._launch(loc, fused=False)
         if self.rank == 0:
             if out is not None:
                 self.buf["out"][:self.sizes[0]].copy_(out)
@@ -328,3 +345,37 @@ def _executor_tensors(executor):
     for name in sorted(vars(executor)):
         if not name.startswith("_"):
             yield from walk(getattr(executor, name))
+
+
+class SpmdUNetEngine(SpmdFluxEngine):
+    """SDXL-class UNet replicas (``exec/unet_exec.py``): x is pulled by the NCHW->NHWC input kernel from rank
+    0's buffer (peer loads), the gather kernel (eps -> Euler -> NCHW) stores into rank 0's output buffer."""
+
+    tma_peer_inputs = ("ctx", "y")
+    kernel_pulled_inputs = ("x",)
+
+    def _latent_channels(self) -> int:
+        return self.ex.in_ch
+
+    def _make_spec(self, B: int) -> dict:
+        bf = torch.bfloat16
+        m = self.ex
+        spec = {"x": ((B, self.C, self.H, self.W), bf), "t": ((B,), bf), "ctx": ((B, self.Lt, m.ctx_dim), bf)}
+        if m.adm is not None:
+            spec["y"] = ((B, m.adm), bf)
+        spec["sig"] = ((B, 2), torch.float32)
+        spec["out"] = ((B, self.C, self.H, self.W), bf)
+        return spec
+
+    def _launch(self, loc: dict, fused: bool):
+        y = loc.get("y")
+        if fused:
+            x_bytes = self.C * self.H * self.W * 2
+            # x_in of the Euler update must be local: one small peer copy of the latent shard
+            if self.rank != 0:
+                self._pull("x")
+            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"],
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                 x_src_ptr=self._src("x", x_bytes))
+            return None
+        return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"])
