@@ -257,6 +257,30 @@ class FluxExecutor(nn.Module):
         self.launches_per_step = n
         return out
 
+    def _maybe_graph(self, key, body) -> None:
+        """Replay the whole step (~410 launches) as ONE CUDA graph once the same buffers have been seen twice.
+        Every pointer the kernels use (inputs, peer mappings, output) is baked into the graph, so the graph is
+        keyed on all of them; any change falls back to eager launches.  Replays release the GIL, which is what
+        lets the in-process engine drive several GPUs from Python threads."""
+        if not self.cuda_graphs:
+            body()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            body()
+            if len(self._graphs) > 32:          # callers that pass fresh buffers every step never re-hit a key
+                self._graphs = {k: v for k, v in self._graphs.items() if v != "seen"}
+            self._graphs[key] = "seen"
+        elif g == "seen":
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+            self._graphs[key] = graph
+            graph.replay()
+        else:
+            g.replay()
+
     # ------------------------------------------------------------------ public entry points
     def _prep(self, x, timesteps, context, y, guidance):
         d = self.device
@@ -295,8 +319,10 @@ class FluxExecutor(nn.Module):
             _, timesteps, context, y, guidance = self._prep(dummy.new_empty((B, 1, 1, 1), dtype=torch.bfloat16),
                                                              timesteps, context, y, guidance)
             ws = self.workspace(B, shape[2], shape[3], context.shape[1])
-            self._run(ws, x_src_ptr, timesteps, context, y, guidance, None, out_ptr=out_ptr,
-                      out_sample_off=out_sample_off)
+            key = ("shard", tuple(shape), x_src_ptr, timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
+                   y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, out_ptr, out_sample_off)
+            self._maybe_graph(key, lambda: self._run(ws, x_src_ptr, timesteps, context, y, guidance, None,
+                                                     out_ptr=out_ptr, out_sample_off=out_sample_off))
 
     @torch.no_grad()
     def denoise_step(self, x, timesteps, context, y, guidance, sigmas, out=None, out_ptr=None, out_sample_off=0,
@@ -316,29 +342,11 @@ class FluxExecutor(nn.Module):
                           out, x_in=x, sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
                           g_ptr=g_src_ptr, x_copy=x if (x_src_ptr is not None and self.fused_embed) else None)
 
-            if not self.cuda_graphs:
-                body()
-                return out
-            # The whole step (~410 launches) is replayed as ONE CUDA graph once the same buffers have been
-            # seen twice: every pointer the kernels use (inputs, peer mappings, output) is baked into the graph,
-            # so it is keyed on all of them and any change falls back to eager launches.
             key = (tuple(x.shape), x.data_ptr(), timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
                    y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, sigmas.data_ptr(),
                    out.data_ptr() if out is not None else 0, out_ptr or 0, out_sample_off, x_src_ptr or 0,
                    t_src_ptr or 0, g_src_ptr or 0)
-            g = self._graphs.get(key)
-            if g is None:
-                body()
-                self._graphs[key] = "seen"
-            elif g == "seen":
-                torch.cuda.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    body()
-                self._graphs[key] = graph
-                graph.replay()
-            else:
-                g.replay()
+            self._maybe_graph(key, body)
             return out
 
 

@@ -379,3 +379,33 @@ class SpmdUNetEngine(SpmdFluxEngine):
                                  x_src_ptr=self._src("x", x_bytes))
             return None
         return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"])
+
+
+class SpmdWanEngine(SpmdFluxEngine):
+    """WAN2.x video DiT replicas (``exec/wan_exec.py``).  ``height``/``width`` are pixel sizes, ``frames`` the
+    number of LATENT frames; the video latent is staged as [B, 16, T, H/8, W/8]."""
+
+    tma_peer_inputs = ("ctx",)
+    kernel_pulled_inputs = ("x", "t")
+
+    def __init__(self, executor, global_batch: int, frames: int, height: int, width: int, txt_len: int, **kw):
+        self.T = frames
+        super().__init__(executor, global_batch, height, width, txt_len, **kw)
+
+    def _latent_channels(self) -> int:
+        return self.ex.params.in_dim
+
+    def _make_spec(self, B: int) -> dict:
+        p, bf = self.ex.params, torch.bfloat16
+        shape = (B, self.C, self.T, self.H, self.W)
+        return {"x": (shape, bf), "t": ((B,), bf), "ctx": ((B, self.Lt, p.text_dim), bf),
+                "sig": ((B, 2), torch.float32), "out": (shape, bf)}
+
+    def _launch(self, loc: dict, fused: bool):
+        if fused:
+            x_bytes = self.C * self.T * self.H * self.W * 2
+            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["sig"],
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                 x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2))
+            return None
+        return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["sig"])
