@@ -9,8 +9,10 @@
 //            row max exchanged through shared memory), so each scheduler has two softmax warps to overlap
 //            the TMEM-load / MUFU / barrier latencies of one with the math of the other.
 //            S_j is read from TMEM once (64 registers per thread), row max with
-//            3-input FMNMX, exp2 with packed FFMA2/FADD2, P_j written to shared memory as a 128B-swizzled
-//            K-major A operand.  O accumulates IN TMEM across all KV tiles (tcgen05.mma accumulate);
+//            3-input FMNMX, exp2 with packed FFMA2/FADD2, P_j (bf16) written back to TENSOR MEMORY with
+//            tcgen05.st and consumed by the PV MMA as a TMEM A operand — the kernel is shared-memory-
+//            bandwidth bound (every 128x128x16 SS-MMA streams 8 KB of operands), so keeping P out of smem
+//            removes a third of that traffic.  O accumulates IN TMEM across all KV tiles (tcgen05.mma accumulate);
 //            it is only rescaled (tcgen05.ld -> mul -> tcgen05.st) when the running row max grows by
 //            more than 2^8 ("lazy rescaling"), which after the first tiles practically never happens.
 // V is consumed as an MN-major B operand straight from its natural [keys, d] layout (no transpose).
@@ -31,10 +33,10 @@ struct AttnCfg {
   static constexpr uint32_t OFF_Q = 0;
   static constexpr uint32_t OFF_K = OFF_Q + QKV_TILE;              // 2 stages
   static constexpr uint32_t OFF_V = OFF_K + 2 * QKV_TILE;          // 2 stages
-  static constexpr uint32_t OFF_P = OFF_V + 2 * QKV_TILE;          // 2 buffers
-  static constexpr uint32_t OFF_BAR = OFF_P + 2 * P_TILE;
+  static constexpr uint32_t OFF_BAR = OFF_V + 2 * QKV_TILE;
+  static constexpr uint32_t TMEM_P = 384;                          // P0 @384, P1 @448 (64 columns = 128 bf16 each)
   static constexpr uint32_t OFF_XCHG = OFF_BAR + 256;              // float[2 (tile parity)][2 (half)][128 rows]
-  static constexpr uint32_t SMEM_BYTES = OFF_XCHG + 2048 + 768;    // D=128: exactly the 227 KB per-CTA limit
+  static constexpr uint32_t SMEM_BYTES = OFF_XCHG + 2048 + 1024;
   static constexpr uint32_t TMEM_COLS = 512;                       // S0 @0, S1 @128, O @256 (D columns)
 };
 
@@ -105,8 +107,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   using Cfg = AttnCfg<D>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN;
   constexpr uint32_t SLICE_BYTES = Cfg::SLICE_BYTES, TILE_BYTES = Cfg::QKV_TILE, P_TILE = Cfg::P_TILE;
-  constexpr uint32_t OFF_Q = Cfg::OFF_Q, OFF_K = Cfg::OFF_K, OFF_V = Cfg::OFF_V, OFF_P = Cfg::OFF_P,
-                     OFF_BAR = Cfg::OFF_BAR, TMEM_COLS = Cfg::TMEM_COLS;
+  constexpr uint32_t OFF_Q = Cfg::OFF_Q, OFF_K = Cfg::OFF_K, OFF_V = Cfg::OFF_V, OFF_BAR = Cfg::OFF_BAR,
+                     TMEM_COLS = Cfg::TMEM_COLS, TMEM_P = Cfg::TMEM_P;
+  (void)P_TILE;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -185,7 +188,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
       constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);     // B (= V) is MN-major, N = D
       const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
-      const uint32_t p_addr = ptx::smem_u32(smem + OFF_P);
       auto issue_qk = [&](int i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
@@ -214,10 +216,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + s * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          const uint64_t a =
-              ptx::make_desc_kmajor_sw128(p_addr + s * P_TILE + (kk >> 2) * SLICE_BYTES + (kk & 3) * 32);
+          // A = P_j from tensor memory: 16 keys = 8 packed 32-bit columns per MMA
           const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
-          ptx::mma_f16_ss(tmem + 256, a, b, IDESC_PV, (j | kk) != 0);
+          ptx::mma_f16_ts(tmem + 256, tmem + TMEM_P + s * 64 + kk * 8, b, IDESC_PV, (j | kk) != 0);
         }
         ptx::tc_commit(&v_empty[s]);
         ptx::tc_commit(&p_empty[s]);
@@ -232,9 +233,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     constexpr int OH = D / 2;                          // output columns owned by this thread
     const uint32_t o_addr = lane_addr + 256 + half * OH;
     float m_used = -INFINITY, l = 0.f;
-    uint8_t* p_row0 = smem + OFF_P + half * SLICE_BYTES + r * 128;
     float* xchg = reinterpret_cast<float*>(smem + Cfg::OFF_XCHG);
-    const int sw = r & 7;
     const unsigned long long sl2 = pack2(scale_log2, scale_log2);
 
     for (int j = 0; j < n_kv; ++j) {
@@ -296,40 +295,32 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
       ptx::mbar_wait(&p_empty[s], ((j >> 1) & 1) ^ 1);   // PV of tile j-2 has consumed this P buffer
-      uint8_t* p_row = p_row0 + s * P_TILE;
       unsigned long long sum2 = pack2(0.f, 0.f);
+      uint32_t pk[32];                                   // this thread's 64 probabilities, bf16x2 packed
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a0, a1;
-          const unsigned long long x2 =
-              fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg);
-          if ((i >> 1) & 1) {
-            // MUFU.EX2 is only 16 lanes/clk/SM on sm_100 (as slow as the two MMAs of this tile): every
-            // second pair goes through a Cody-Waite + degree-4 polynomial on the FMA pipe instead.
-            exp2_poly2(x2, a0, a1);
-          } else {
-            unpack2(x2, a0, a1);
-            a0 = ex2f(a0);
-            a1 = ex2f(a1);
-          }
-          sum2 = add2(sum2, pack2(a0, a1));
-          __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+      for (int i = 0; i < 64; i += 2) {
+        float a0, a1;
+        const unsigned long long x2 =
+            fma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, mneg);
+        if ((i >> 1) & 1) {
+          // MUFU.EX2 is only 16 lanes/clk/SM on sm_100 (as slow as the two MMAs of this tile): every
+          // second pair goes through a Cody-Waite + degree-4 polynomial on the FMA pipe instead.
+          exp2_poly2(x2, a0, a1);
+        } else {
+          unpack2(x2, a0, a1);
+          a0 = ex2f(a0);
+          a1 = ex2f(a1);
         }
-        // 32 keys = 64 bytes = four 16-byte chunks of this row inside this half's 64-key slice
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c * 4 + q) ^ sw;
-          *reinterpret_cast<uint4*>(p_row + chunk * 16) = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
+        sum2 = add2(sum2, pack2(a0, a1));
+        __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
       }
+      ptx::tmem_st_32x32b_x32(lane_addr + TMEM_P + s * 64 + half * 32, pk);
+      ptx::tmem_st_wait();
       float s0, s1;
       unpack2(sum2, s0, s1);
       l += s0 + s1;
-      ptx::fence_proxy_async_smem();     // P_j (generic-proxy stores) visible to the tensor core (async proxy)
+      ptx::tc_fence_before();            // P_j (tcgen05.st) ordered before the PV MMA that the arrive releases
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[s]);
     }
