@@ -111,7 +111,11 @@ class FluxExecutor(nn.Module):
                 if w.shape[0] % 128 or w.shape[1] % 128:
                     W[name + ".w"] = w
                     continue
-                W[name + ".q"], W[name + ".sf"] = ops.quantize_mxfp8(w)
+                # B-tile width the GEMM will use: 256 (single accumulator) for the fused QKV epilogues,
+                # 224 (double-buffered accumulators) for everything else
+                tile = 256 if name.split(".")[-1] in ("qkv", "l1") else 224
+                W[name + ".q"], W[name + ".sf"] = ops.quantize_mxfp8(w, tile)
+                W[name + ".tile"] = tile
                 del w
             torch.cuda.empty_cache()
         self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
@@ -129,7 +133,7 @@ class FluxExecutor(nn.Module):
         self._graphs.clear()
 
     def weight_bytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self.W.values() if t is not None)
+        return sum(t.numel() * t.element_size() for t in self.W.values() if isinstance(t, torch.Tensor))
 
     # ------------------------------------------------------------------ workspaces
     def workspace(self, B: int, H: int, Wd: int, Lt: int) -> dict:
@@ -167,7 +171,7 @@ class FluxExecutor(nn.Module):
         W = self.W
         if name + ".q" in W:
             aq, sfa = ops.quantize_mxfp8(a)
-            ops.gemm_fp8(aq, sfa, W[name + ".q"], W[name + ".sf"], mode, bias=W[name + ".b"], **kw)
+            ops.gemm_fp8(aq, sfa, W[name + ".q"], W[name + ".sf"], mode, W[name + ".tile"], bias=W[name + ".b"], **kw)
             return 3
         ops.gemm(a, W[name + ".w"], mode, bias=W[name + ".b"], **kw)
         return 1

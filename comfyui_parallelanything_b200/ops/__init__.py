@@ -123,23 +123,27 @@ def groupnorm_silu(x_nhwc, gamma, beta, groups: int = 32, eps: float = 1e-5, sil
 
 
 # ----------------------------------------------------------------------------- MXFP8 (block-scaled fp8)
-def quantize_mxfp8(x: torch.Tensor):
-    """bf16 [.., rows, K] -> (e4m3 bytes, UE8M0 scale chunks) for the block-scaled tcgen05 GEMM (K % 128 == 0)."""
-    q, sf = require().quantize_mxfp8(x)
+def quantize_mxfp8(x: torch.Tensor, tile_rows: int = 128):
+    """bf16 [.., rows, K] -> (e4m3 bytes, UE8M0 scale chunks) for the block-scaled tcgen05 GEMM (K % 128 == 0).
+    ``tile_rows``: 128 for activations; for weights the B-tile width the GEMM will use (224 generic / 256 QKV)."""
+    q, sf = require().quantize_mxfp8(x, tile_rows)
     return q, sf
 
 
-def dequantize_mxfp8(q: torch.Tensor, sf: torch.Tensor) -> torch.Tensor:
+def dequantize_mxfp8(q: torch.Tensor, sf: torch.Tensor, tile_rows: int = 128) -> torch.Tensor:
     """Reference decode of ``quantize_mxfp8`` output (fp32), used by the numerics checks."""
     if q.dim() == 2:
         q = q.unsqueeze(0)
     b, rows, k = q.shape
-    mt, kc = (rows + 127) // 128, k // 128
-    e = sf.view(b, mt, kc, 32, 4, 4).permute(0, 1, 4, 3, 2, 5).reshape(b, mt * 128, kc * 4)[:, :rows].float() - 127.0
+    cpt, kc = (tile_rows + 127) // 128, k // 128
+    tiles = (rows + tile_rows - 1) // tile_rows
+    e = sf.view(b, tiles, cpt, kc, 32, 4, 4).permute(0, 1, 2, 5, 4, 3, 6).reshape(b, tiles, cpt * 128, kc * 4)
+    e = e[:, :, :tile_rows].reshape(b, tiles * tile_rows, kc * 4)[:, :rows].float() - 127.0
     vals = q.view(torch.float8_e4m3fn).float().view(b, rows, k // 32, 32)
     return (vals * torch.exp2(e)[..., None]).reshape(b, rows, k)
 
 
-def gemm_fp8(a_q, sfa, w_q, sfb, mode: str = "bias", **kw) -> None:
-    """Block-scaled fp8 GEMM: same epilogues / keyword arguments as ``gemm`` (bf16 outputs)."""
-    require().gemm_fp8(a_q, sfa, w_q, sfb, EPI[mode], **kw)
+def gemm_fp8(a_q, sfa, w_q, sfb, mode: str = "bias", w_tile: int = 224, **kw) -> None:
+    """Block-scaled fp8 GEMM: same epilogues / keyword arguments as ``gemm`` (bf16 outputs).  ``w_tile`` must be
+    the ``tile_rows`` the weight was quantised with (224 generic, 256 for the fused QKV epilogue)."""
+    require().gemm_fp8(a_q, sfa, w_q, sfb, EPI[mode], w_tile, **kw)

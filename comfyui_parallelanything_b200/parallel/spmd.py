@@ -287,7 +287,7 @@ def broadcast_executor_weights(executor, src: int = 0, group=None, bucket_bytes:
     multicast / NVLS when NCCL enables it) in ``bucket_bytes`` buckets — no host bounce, unlike the
     reference's ``source.cpu()`` + per-key H2D clone (/root/reference/any_device_parallel.py:600-663).
     Returns the number of bytes received/sent."""
-    tensors = [t for t in _executor_tensors(executor) if t is not None and t.is_cuda]
+    tensors = [t for t in _executor_tensors(executor) if isinstance(t, torch.Tensor) and t.is_cuda]
     total, bucket, size = 0, [], 0
 
     def flush():

@@ -85,7 +85,7 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
 }
 
 // MXFP8: A_q / W_q are uint8 (e4m3 bit patterns) contiguous, sfa / sfb uint8 scale chunks (see gemm_mxfp8.cu)
-static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, py::kwargs kw) {
+static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, int w_tile, py::kwargs kw) {
   TORCH_CHECK(A.is_cuda() && A.is_contiguous() && W.is_contiguous() && A.element_size() == 1 && W.element_size() == 1,
               "gemm_fp8: contiguous 1-byte operands required");
   c10::cuda::CUDAGuard guard(A.device());
@@ -98,11 +98,12 @@ static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, py::k
   p.mode = mode;
   parse_epilogue(kw, p, /*check_shape=*/true);
   parse_modes(mode, kw, p);
-  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, cur_stream()), "gemm_mxfp8");
+  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, w_tile, cur_stream()),
+        "gemm_mxfp8");
 }
 
 // bf16 [B, rows, K] / [rows, K] view -> (e4m3 bytes [B, rows, K], scale chunks)
-static std::vector<Tensor> quantize_mxfp8(Tensor x) {
+static std::vector<Tensor> quantize_mxfp8(Tensor x, int tile_rows) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.scalar_type() == at::kBFloat16, "quantize_mxfp8: bf16 input");
   int b, rows;
@@ -112,8 +113,10 @@ static std::vector<Tensor> quantize_mxfp8(Tensor x) {
   TORCH_CHECK(K % 128 == 0, "quantize_mxfp8: K must be a multiple of 128");
   auto o8 = x.options().dtype(at::kByte);
   Tensor q = x.dim() == 2 ? at::empty({rows, K}, o8) : at::empty({b, rows, K}, o8);
-  Tensor sf = at::zeros({(int64_t)b * ((rows + 127) / 128) * (K / 128) * 512}, o8);
-  check(pa::quantize_mxfp8_rows(x.data_ptr(), ld, bs, q.data_ptr(), sf.data_ptr(), b, rows, K, cur_stream()),
+  const int64_t chunks = (int64_t)((rows + tile_rows - 1) / tile_rows) * ((tile_rows + 127) / 128);
+  Tensor sf = at::zeros({(int64_t)b * chunks * (K / 128) * 512}, o8);
+  check(pa::quantize_mxfp8_rows(x.data_ptr(), ld, bs, q.data_ptr(), sf.data_ptr(), b, rows, K, tile_rows,
+                                cur_stream()),
         "quantize_mxfp8_rows");
   return {q, sf};
 }
@@ -371,8 +374,9 @@ static void wait_flags(Tensor flags, int first, int n, uint32_t value, long long
 PYBIND11_MODULE(_C, m) {
   m.doc() = "comfyui-parallelanything_b200 native library (sm_100a kernels + runtime)";
   m.def("gemm", &gemm, py::arg("A"), py::arg("W"), py::arg("mode"));
-  m.def("gemm_fp8", &gemm_fp8, py::arg("A"), py::arg("sfa"), py::arg("W"), py::arg("sfb"), py::arg("mode"));
-  m.def("quantize_mxfp8", &quantize_mxfp8);
+  m.def("gemm_fp8", &gemm_fp8, py::arg("A"), py::arg("sfa"), py::arg("W"), py::arg("sfb"), py::arg("mode"),
+        py::arg("w_tile"));
+  m.def("quantize_mxfp8", &quantize_mxfp8, py::arg("x"), py::arg("tile_rows") = 128);
   m.def("conv", &conv, py::arg("x"), py::arg("w"), py::arg("taps"), py::arg("stride"), py::arg("mode"));
   m.def("layernorm_modulate", &layernorm_modulate, py::arg("x"), py::arg("out"), py::arg("scale") = py::none(),
         py::arg("shift") = py::none(), py::arg("gamma") = py::none(), py::arg("beta") = py::none(),

@@ -22,8 +22,9 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
 
 // block-scaled FP8 (MXFP8) GEMM + quantiser (csrc/kernels/gemm_mxfp8.cu)
 int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
-                        cudaStream_t st);
-int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, cudaStream_t st);
+                        int tile_rows, cudaStream_t st);
+int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
+               cudaStream_t st);
 
 // out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
 int layernorm_modulate(const void* x, long long ldx, long long x_bstride, void* out, long long ldo,

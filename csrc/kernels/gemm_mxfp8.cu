@@ -17,19 +17,25 @@
 
 namespace pa {
 
-template <int BN>
+// Tile shapes.  A 128x128x32 SS-MMA streams 8 KB of operands per 64 tensor cycles = the whole 128 B/clk
+// shared-memory bandwidth of an SM, so N = 128 tiles run at half of the fp8 peak; N >= 224 is needed.  TMEM has
+// 512 columns: double-buffered accumulators (2 x N) + scale factors (4 + 4*ceil(N/128)) fit for N <= 240
+// -> <224, 2> for the generic epilogues; the fused QKV epilogue needs whole 128-wide heads per tile
+// -> <256, 1> (single accumulator, epilogue not overlapped with the next tile's main loop).
+template <int BN, int ACC>
 struct Mx8Cfg {
   static constexpr int BM = 128, BK = 128;                       // BK in elements == bytes
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int NCHUNK = (BN + 127) / 128;                // 128-row scale-factor chunks per B tile
+  static constexpr int STAGES = 4;
   static constexpr uint32_t A_BYTES = BM * BK, B_BYTES = BN * BK;
-  static constexpr uint32_t SFA_BYTES = 512, SFB_BYTES = 512 * (BN / 128);
+  static constexpr uint32_t SFA_BYTES = 512, SFB_BYTES = 512 * NCHUNK;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
   static constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
-  static constexpr uint32_t ACC_COLS = 2 * BN;                   // double-buffered accumulators
-  static constexpr uint32_t SF_COL = ACC_COLS;                   // SFA: 4 columns, SFB: 4 * BN/128 columns
+  static constexpr uint32_t ACC_COLS = ACC * BN;
+  static constexpr uint32_t SF_COL = ACC_COLS;                   // SFA: 4 columns, SFB: 4 * NCHUNK columns
   static constexpr uint32_t TMEM_COLS = 512;
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_STRIDE + 256 + 1024;
-  static_assert(ACC_COLS + 4 + 4 * (BN / 128) <= 512, "TMEM budget");
+  static_assert(ACC_COLS + 4 + 4 * NCHUNK <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -48,12 +54,12 @@ __device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
+template <int BN, int ACC>
 __global__ void __launch_bounds__(256, 1)
 gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const uint8_t* __restrict__ sfa, const uint8_t* __restrict__ sfb, const GemmParams p) {
-  using Cfg = Mx8Cfg<BN>;
-  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  using Cfg = Mx8Cfg<BN, ACC>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, NCHUNK = Cfg::NCHUNK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_STRIDE);
@@ -80,6 +86,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::fence_proxy_async_smem();
   }
   if (warp == 2) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  static_assert(ACC == 1 || ACC == 2, "one or two accumulator stages");
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -110,7 +117,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         decode(t, mt, nt);
         const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
         const uint8_t* sfa_t = sfa + static_cast<long long>(mt) * num_k * 512;
-        const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * (BN / 128) * num_k * 512;
+        const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * NCHUNK * num_k * 512;
         for (int kb = 0; kb < num_k; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
@@ -119,7 +126,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
           bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES, sfa_t + static_cast<long long>(kb) * 512, 512, &full[stage]);
 #pragma unroll
-          for (int j = 0; j < BN / 128; ++j)
+          for (int j = 0; j < NCHUNK; ++j)
             bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES + 512 + j * 512,
                          sfb_t + (static_cast<long long>(j) * num_k + kb) * 512, 512, &full[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -133,8 +140,9 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int it = 0;
       const uint32_t sfa_t = tmem_base + Cfg::SF_COL, sfb_t = tmem_base + Cfg::SF_COL + 4;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        ptx::mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        const int acc = ACC == 2 ? (it & 1) : 0;
+        const uint32_t acc_phase = ACC == 2 ? ((it >> 1) & 1) : (it & 1);
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -144,7 +152,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // scale factors of this K-block: smem -> TMEM (ordered with the MMAs in the tensor-core pipe)
           ptx::tmem_cp_32x128b_warpx4(sfa_t, make_sf_desc(sa + Cfg::A_BYTES + Cfg::B_BYTES));
 #pragma unroll
-          for (int j = 0; j < BN / 128; ++j)
+          for (int j = 0; j < NCHUNK; ++j)
             ptx::tmem_cp_32x128b_warpx4(sfb_t + 4 * j, make_sf_desc(sa + Cfg::A_BYTES + Cfg::B_BYTES + 512 + j * 512));
           const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);
           const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES);
@@ -168,8 +176,8 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       decode(t, mt, nt);
       const int b = mt / m_per_batch;
       const int row = (mt - b * m_per_batch) * BM + r_in_tile;
-      const int acc = it & 1;
-      ptx::mbar_wait(&tfull[acc], (it >> 1) & 1);
+      const int acc = ACC == 2 ? (it & 1) : 0;
+      ptx::mbar_wait(&tfull[acc], ACC == 2 ? ((it >> 1) & 1) : (it & 1));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
       epilogue_tile<BN>(p, taddr, b, row, row < p.rows, nt * BN);
@@ -190,11 +198,15 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // bf16 [batch, rows, K] (strided) -> e4m3 [batch, rows, K] + UE8M0 scales in the chunk layout.
 // One thread per 32-element block.  scale = 2^ceil(log2(amax / 448)); rows >= `rows` of the last 128-row
 // tile keep scale byte 0 (the caller zero-initialises the SF buffer) and are zero-filled by TMA.
+// `tile_rows`: rows per GEMM tile of this operand (128 for A; the B tile width for weights).  Scale chunks
+// are grouped per tile: chunk(tile t, j) covers rows [t*tile_rows + 128 j, ... + 128) of that tile.
 __global__ void quantize_mxfp8_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long x_bs,
-                                      uint8_t* __restrict__ q, uint8_t* __restrict__ sf, int batch, int rows, int K) {
+                                      uint8_t* __restrict__ q, uint8_t* __restrict__ sf, int batch, int rows, int K,
+                                      int tile_rows) {
   const int kblocks = K >> 5;
   const long long total = static_cast<long long>(batch) * rows * kblocks;
-  const int m_tiles = (rows + 127) >> 7, kchunks = K >> 7;
+  const int cpt = (tile_rows + 127) >> 7;                          // chunks per tile
+  const int m_tiles = ((rows + tile_rows - 1) / tile_rows) * cpt, kchunks = K >> 7;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int kb = static_cast<int>(i % kblocks);
@@ -234,45 +246,50 @@ __global__ void quantize_mxfp8_kernel(const __nv_bfloat16* __restrict__ x, long 
     uint4* dst = reinterpret_cast<uint4*>(q + (static_cast<long long>(b) * rows + r) * K + kb * 32);
     dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-    const int mt = r >> 7, r128 = r & 127;
+    const int tile = r / tile_rows, rt = r - tile * tile_rows;
+    const int mt = tile * cpt + (rt >> 7), r128 = rt & 127;
     const long long chunk = (static_cast<long long>(b) * m_tiles + mt) * kchunks + (kb >> 2);
     sf[chunk * 512 + (r128 & 31) * 16 + (r128 >> 5) * 4 + (kb & 3)] = static_cast<uint8_t>(e + 127);
   }
 }
 
 int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
-                        cudaStream_t st) {
-  if (K % 128 || ldx % 8 || x_bs % 8) return -1;
+                        int tile_rows, cudaStream_t st) {
+  if (K % 128 || ldx % 8 || x_bs % 8 || tile_rows < 128 || tile_rows > 256) return -1;
   const long long total = static_cast<long long>(batch) * rows * (K / 32);
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
   quantize_mxfp8_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), ldx, x_bs,
-                                                static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), batch, rows, K);
+                                                static_cast<uint8_t*>(q), static_cast<uint8_t*>(sf), batch, rows, K,
+                                                tile_rows);
   return (int)cudaGetLastError();
 }
 
-template <int BN>
+template <int BN, int ACC>
 static int launch_mx8(const CUtensorMap& ta, const CUtensorMap& tb, const void* sfa, const void* sfb,
                       const GemmParams& p, int tiles, cudaStream_t st) {
-  using Cfg = Mx8Cfg<BN>;
+  using Cfg = Mx8Cfg<BN, ACC>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_kernel<BN, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_mxfp8_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, static_cast<const uint8_t*>(sfa),
-                                                            static_cast<const uint8_t*>(sfb), p);
+  gemm_mxfp8_kernel<BN, ACC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, static_cast<const uint8_t*>(sfa),
+                                                                 static_cast<const uint8_t*>(sfb), p);
   return (int)cudaGetLastError();
 }
 
-// A: e4m3 [batch, rows, K] contiguous, W: e4m3 [N, K] contiguous (N % 128 == 0), scales in chunk layout.
-int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, cudaStream_t st) {
-  if (p.K % 128 || p.N % 128) return -10;
-  constexpr int BN = 128;
+// A: e4m3 [batch, rows, K] contiguous (scales: 128-row tiles), W: e4m3 [N, K] contiguous with scales grouped for
+// `w_tile` = 224 (generic epilogues, double-buffered accumulators), 256 (fused QKV epilogue) or 128.
+int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
+               cudaStream_t st) {
+  if (p.K % 128 || p.N % 32) return -10;
+  if (w_tile != 128 && w_tile != 224 && w_tile != 256) return -11;
+  if (p.mode == EPI_QKV_ROPE && w_tile == 224) return -12;
   CUtensorMap ta, tb;
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
@@ -283,11 +300,13 @@ int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, G
   {
     uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
     uint64_t str[2] = {1, (uint64_t)p.K};
-    uint32_t box[2] = {128, (uint32_t)BN};
+    uint32_t box[2] = {128, (uint32_t)w_tile};
     if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
   }
-  const int tiles = ((p.rows + 127) / 128) * p.batch * (p.N / BN);
-  return launch_mx8<BN>(ta, tb, sfa, sfb, p, tiles, st);
+  const int tiles = ((p.rows + 127) / 128) * p.batch * ((p.N + w_tile - 1) / w_tile);
+  if (w_tile == 224) return launch_mx8<224, 2>(ta, tb, sfa, sfb, p, tiles, st);
+  if (w_tile == 256) return launch_mx8<256, 1>(ta, tb, sfa, sfb, p, tiles, st);
+  return launch_mx8<128, 2>(ta, tb, sfa, sfb, p, tiles, st);
 }
 
 }  // namespace pa
