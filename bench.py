@@ -144,8 +144,18 @@ def timed(fn, steps: int, warmup: int, world: int):
     return max_over_ranks(e0.elapsed_time(e1), world) / steps
 
 
+_REAL_STDOUT = sys.stdout
+
+
 def emit(obj: dict):
-    print(json.dumps(obj), flush=True)
+    """The ONE JSON line goes to the real stdout; everything else (the reference's ``print`` chatter, our
+    logger) is routed to stderr by ``quiet_stdout`` so the line stays machine-readable."""
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
+def quiet_stdout():
+    sys.stdout = sys.stderr
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -361,6 +371,7 @@ def main() -> int:
                     help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8); default bf16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

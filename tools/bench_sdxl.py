@@ -38,6 +38,7 @@ def main() -> int:
     ap.add_argument("--config", type=int, default=2, choices=[2, 5])
     ap.add_argument("--batch", type=int, default=0)
     a = ap.parse_args()
+    hb.quiet_stdout()
     import torch
     rank, world, local = hb.dist_env()
     B = a.batch or (16 if a.config == 2 else 32)
