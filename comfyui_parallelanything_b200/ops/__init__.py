@@ -106,12 +106,16 @@ def timestep_embedding(t: torch.Tensor, dim: int = 256, time_factor: float = 100
     return out
 
 
-def attention(q, k, v, out=None, scale: Optional[float] = None):
-    """q,k,v: [B,H,L,128] bf16 contiguous -> out [B, Lq, H*128]."""
+ATTENTION_VARIANT = int(os.environ.get("PA_ATTENTION", "2"))    # 1: one query tile per CTA, 2: ping-pong (two)
+
+
+def attention(q, k, v, out=None, scale: Optional[float] = None, variant: Optional[int] = None):
+    """q,k,v: [B,H,L,D] bf16 views (D = 64 / 128, innermost contiguous) -> out [B, Lq, H*D]."""
     b, h, lq, d = q.shape
     if out is None:
         out = torch.empty(b, lq, h * d, dtype=torch.bfloat16, device=q.device)
-    require().attention(q, k, v, out, float(scale if scale is not None else d ** -0.5))
+    require().attention(q, k, v, out, float(scale if scale is not None else d ** -0.5),
+                        ATTENTION_VARIANT if variant is None else variant)
     return out
 
 

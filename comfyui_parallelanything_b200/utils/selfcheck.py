@@ -196,10 +196,16 @@ def gemm_euler_unpatch():
 # ------------------------------------------------------------------------------ attention
 def _attn_case(name, B, H, Lq, Lk, tol=0.02):
     q, k, v = _rand(B, H, Lq, 128), _rand(B, H, Lk, 128, seed=1), _rand(B, H, Lk, 128, seed=2)
-    out = ops.attention(q, k, v)
     want = F.scaled_dot_product_attention(q.float(), k.float(), v.float())
     want = want.transpose(1, 2).reshape(B, Lq, H * 128)
-    return _cmp(name, out, want, tol)
+    worst = None
+    for variant in (1, 2):                       # one query tile per CTA / ping-pong with two
+        out = ops.attention(q, k, v, variant=variant)
+        r = _cmp(name, out, want, tol)
+        r["variant"] = variant
+        if worst is None or not r["ok"] or (worst["ok"] and r["mean_rel"] > worst["mean_rel"]):
+            worst = r
+    return worst
 
 
 @check
@@ -425,16 +431,40 @@ def attention_d64_strided():
     B, H, L, D = 2, 10, 1024, 64
     qkv = _rand(B, L, 3, H, D)
     q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))       # [B, H, L, D] views, no copies
-    out = ops.attention(q, k, v)
     want = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, L, H * D)
-    r = _cmp("attention_d64_strided", out, want, 0.02)
     kc, vc = _rand(B, 77, H, D, seed=5).permute(0, 2, 1, 3), _rand(B, 77, H, D, seed=6).permute(0, 2, 1, 3)
-    out2 = ops.attention(q, kc, vc)
     want2 = F.scaled_dot_product_attention(q.float(), kc.float(), vc.float()).transpose(1, 2).reshape(B, L, H * D)
-    r2 = _cmp("cross77", out2, want2, 0.02)
-    r["cross77_mean_rel"] = r2["mean_rel"]
-    r["ok"] = r["ok"] and r2["ok"]
+    r = None
+    for variant in (1, 2):
+        ra = _cmp("attention_d64_strided", ops.attention(q, k, v, variant=variant), want, 0.02)
+        rb = _cmp("cross77", ops.attention(q, kc, vc, variant=variant), want2, 0.02)
+        ra["cross77_mean_rel"] = rb["mean_rel"]
+        ra["variant"] = variant
+        ra["ok"] = ra["ok"] and rb["ok"]
+        if r is None or not ra["ok"]:
+            r = ra
     return r
+
+
+@check
+def attention_speed():
+    """Device-timed FLUX-shaped attention (B=2, 24 heads, 4608 tokens) for both kernel variants."""
+    q, k, v = (_rand(2, 24, 4608, 128, seed=i) for i in range(3))
+    out = torch.empty(2, 4608, 3072, dtype=torch.bfloat16, device=_dev())
+    res = {"name": "attention_speed", "ok": True}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for variant in (1, 2):
+        for _ in range(3):
+            ops.attention(q, k, v, out=out, variant=variant)
+        e0.record()
+        for _ in range(10):
+            ops.attention(q, k, v, out=out, variant=variant)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        res[f"v{variant}_ms"] = round(ms, 4)
+        res[f"v{variant}_tflops"] = round(4.0 * 2 * 24 * 4608 * 4608 * 128 / ms / 1e9, 1)
+    return res
 
 
 @check

@@ -318,7 +318,7 @@ static void add_(Tensor a, Tensor b, Tensor out) {
   check(pa::add_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), cur_stream()), "add");
 }
 
-static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale) {
+static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, int variant) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4, "q/k/v must be [B, H, L, D] views");
   const int D = (int)q.size(3);
@@ -329,9 +329,9 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale) {
   long long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
   long long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
   long long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
-  check(pa::attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
-                           (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale,
-                           cur_stream()),
+  auto fn = variant == 2 ? pa::attention2_bf16 : pa::attention_bf16;
+  check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0), (int)q.size(0),
+           (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale, cur_stream()),
         "attention");
 }
 
@@ -393,7 +393,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("softmax_rows", &softmax_rows);
   m.def("silu", &silu_);
   m.def("add", &add_);
-  m.def("attention", &attention);
+  m.def("attention", &attention, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("scale"),
+        py::arg("variant") = 1);
   m.def("groupnorm_silu", &groupnorm_silu);
   m.def("cfg_euler_store", &cfg_euler_store);
   m.def("signal_flags", &signal_flags);

@@ -1,0 +1,380 @@
+// Attention, ping-pong variant: TWO 128-row query tiles per CTA, each owned by its own softmax warpgroup,
+// sharing every K/V tile.  Profiling of the one-tile kernel (attention.cu) showed its period is the serial
+// chain  S-tile TMEM read -> max/exp -> P write  of a single warpgroup (~2.5x the MMA time, tensor pipe 41 %);
+// with two tiles in flight the tensor pipe works on tile B (P.V and the next Q.K^T) while warpgroup A drains
+// S_A from tensor memory, and vice versa.
+//
+//   warp 0      TMA producer (Q_A, Q_B once; K_j, V_j rings)          warp 2   TMEM allocator
+//   warp 1      tcgen05.mma issuer                                     warps 4-7 / 8-11  softmax of tile A / B
+//   TMEM        S_A @0, S_B @128 (fp32, 128 cols), O_A @256, O_B @384; P_X (bf16) overwrites the first 64
+//               columns of S_X once S_X sits in registers and feeds the P.V MMA as a TMEM A operand.
+//   registers   setmaxnreg: 56 for the producer/MMA warpgroup, 208 for the softmax warpgroups.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../common/host.h"
+#include "../common/ptx.cuh"
+
+namespace pa {
+namespace a2 {
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for two packed floats on the FMA pipe (see attention.cu)
+__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, float& r1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const unsigned long long x = pack2(x0, x1);
+  const unsigned long long xr = add2(x, pack2(12582912.0f, 12582912.0f));
+  const unsigned long long nf = add2(xr, pack2(-12582912.0f, -12582912.0f));
+  float n0, n1;
+  unpack2(nf, n0, n1);
+  const unsigned long long f = add2(x, pack2(-n0, -n1));
+  unsigned long long p = pack2(0.009618129f, 0.009618129f);
+  p = fma2(p, f, pack2(0.05550411f, 0.05550411f));
+  p = fma2(p, f, pack2(0.2402265f, 0.2402265f));
+  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, xr0, xr1;
+  unpack2(p, p0, p1);
+  unpack2(xr, xr0, xr1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xr0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xr1) << 23));
+}
+
+template <int D>
+struct Cfg {
+  static constexpr int BN = 128;
+  static constexpr uint32_t SLICE = 128 * 64 * 2;
+  static constexpr uint32_t TILE = 128 * D * 2;
+  static constexpr uint32_t OFF_Q = 0;                      // Q_A, Q_B
+  static constexpr uint32_t OFF_K = 2 * TILE;               // 2 stages
+  static constexpr uint32_t OFF_V = 4 * TILE;               // 2 stages
+  static constexpr uint32_t OFF_BAR = 6 * TILE;
+  static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
+};
+
+template <int D>
+__global__ void __launch_bounds__(384, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
+                  long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
+  using C = Cfg<D>;
+  constexpr int BN = C::BN;
+  constexpr uint32_t SLICE = C::SLICE, TILE = C::TILE;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* k_full = bars + 1;      // 2
+  uint64_t* k_empty = bars + 3;     // 2
+  uint64_t* v_full = bars + 5;      // 2
+  uint64_t* v_empty = bars + 7;     // 2
+  uint64_t* s_full = bars + 9;      // 2 (tile A, B)
+  uint64_t* p_full = bars + 11;     // 2
+  uint64_t* o_full = bars + 13;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int bh = blockIdx.y;
+  const int n_kv = (Lk + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&k_full[i], 1);
+      ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);
+      ptx::mbar_init(&v_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&o_full[i], 1);
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    ptx::setmaxnreg_dec<56>();
+    if (warp == 0 && lane == 0) {
+      // ===================== TMA producer =====================
+      const int hb = bh / H, hh = bh - hb * H;
+      ptx::mbar_arrive_expect_tx(q_full, 2 * TILE);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int sl = 0; sl < D / 64; ++sl)
+          ptx::tma_load_4d(smem + C::OFF_Q + t * TILE + sl * SLICE, &tmQ, q_full, sl * 64, q0 + t * 128, hh, hb);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&k_full[s], TILE);
+#pragma unroll
+        for (int sl = 0; sl < D / 64; ++sl)
+          ptx::tma_load_4d(smem + C::OFF_K + s * TILE + sl * SLICE, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
+        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+        ptx::mbar_arrive_expect_tx(&v_full[s], TILE);
+#pragma unroll
+        for (int sl = 0; sl < D / 64; ++sl)
+          ptx::tma_load_4d(smem + C::OFF_V + s * TILE + sl * SLICE, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
+      constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);
+      auto qk = [&](int x, int i) {            // S_X = Q_X K_i^T
+        const uint32_t q_addr = ptx::smem_u32(smem + C::OFF_Q + x * TILE);
+        const uint32_t k_addr = ptx::smem_u32(smem + C::OFF_K + (i & 1) * TILE);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * SLICE + (kk & 3) * 32;
+          ptx::mma_f16_ss(tmem + x * 128, ptx::make_desc_kmajor_sw128(q_addr + off),
+                          ptx::make_desc_kmajor_sw128(k_addr + off), IDESC_QK, kk != 0);
+        }
+        ptx::tc_commit(&s_full[x]);
+      };
+      ptx::mbar_wait(q_full, 0);
+      ptx::mbar_wait(&k_full[0], 0);
+      ptx::tc_fence_after();
+      qk(0, 0);
+      qk(1, 0);
+      ptx::tc_commit(&k_empty[0]);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        ptx::mbar_wait(&v_full[st], (j >> 1) & 1);
+        const uint32_t v_addr = ptx::smem_u32(smem + C::OFF_V + st * TILE);
+#pragma unroll 1
+        for (int x = 0; x < 2; ++x) {
+          ptx::mbar_wait(&p_full[x], j & 1);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE, 1024);
+            ptx::mma_f16_ts(tmem + 256 + x * 128, tmem + x * 128 + kk * 8, b, IDESC_PV, (j | kk) != 0);
+          }
+          ptx::tc_commit(&o_full[x]);
+          if (x == 1) ptx::tc_commit(&v_empty[st]);
+          if (j + 1 < n_kv) {
+            if (x == 0) {
+              ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+              ptx::tc_fence_after();
+            }
+            qk(x, j + 1);                      // overwrites S_X / P_X: ordered after P_X.V in the tensor pipe
+            if (x == 1) ptx::tc_commit(&k_empty[(j + 1) & 1]);
+          }
+        }
+      }
+    }
+  } else {
+    ptx::setmaxnreg_inc<208>();
+    // ===================== softmax warpgroups =====================
+    const int x = (warp - 4) >> 2;                      // query tile of this warpgroup
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t s_addr = lane_addr + x * 128;
+    const uint32_t o_addr = lane_addr + 256 + x * 128;
+    float m_used = -INFINITY, l = 0.f;
+    const unsigned long long sl2 = pack2(scale_log2, scale_log2);
+
+    for (int j = 0; j < n_kv; ++j) {
+      ptx::mbar_wait(&s_full[x], j & 1);
+      ptx::tc_fence_after();
+      uint32_t sv[128];
+      {
+        uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        uint32_t(&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
+        uint32_t(&c3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
+        ptx::tmem_ld_32x32b_x32(s_addr, c0);
+        ptx::tmem_ld_32x32b_x32(s_addr + 32, c1);
+        ptx::tmem_ld_32x32b_x32(s_addr + 64, c2);
+        ptx::tmem_ld_32x32b_x32(s_addr + 96, c3);
+        ptx::tmem_ld_wait();
+      }
+      const int kv_left = Lk - j * BN;
+      if (kv_left < BN) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= kv_left) sv[i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; i += 8) {
+        mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
+      }
+      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_used));
+      const bool need = (m_new - m_used) * scale_log2 > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2f((m_used - m_new) * scale_log2) : 1.0f;
+        if (need) m_used = m_new;
+        l *= alpha;
+        if (j > 0) {
+          ptx::mbar_wait(&o_full[x], (j - 1) & 1);
+          ptx::tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t t[32];
+            ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            ptx::tmem_st_32x32b_x32(o_addr + c * 32, t);
+          }
+          ptx::tmem_st_wait();
+        }
+      }
+      const float mneg_f = -m_used * scale_log2;
+      const unsigned long long mneg = pack2(mneg_f, mneg_f);
+      unsigned long long sum2 = pack2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a0, a1;
+          const unsigned long long x2 =
+              fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg);
+          if ((i >> 1) & 1) {
+            exp2_poly2(x2, a0, a1);
+          } else {
+            unpack2(x2, a0, a1);
+            a0 = ex2f(a0);
+            a1 = ex2f(a1);
+          }
+          sum2 = add2(sum2, pack2(a0, a1));
+          __nv_bfloat162 hv = __floats2bfloat162_rn(a0, a1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hv);
+        }
+        ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);    // P_X: keys 32c..32c+31 -> packed columns 16c..16c+15
+      }
+      ptx::tmem_st_wait();
+      float s0, s1;
+      unpack2(sum2, s0, s1);
+      l += s0 + s1;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+    }
+
+    ptx::mbar_wait(&o_full[x], (n_kv - 1) & 1);
+    ptx::tc_fence_after();
+    const int q_row = q0 + x * 128 + r;
+    const float inv = 1.0f / l;
+    const int b = bh / H, h = bh - b * H;
+    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t t[32];
+      ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
+      ptx::tmem_ld_wait();
+      if (q_row < Lq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          __nv_bfloat162 a0 = __floats2bfloat162_rn(__uint_as_float(t[i]) * inv, __uint_as_float(t[i + 1]) * inv);
+          __nv_bfloat162 a1 = __floats2bfloat162_rn(__uint_as_float(t[i + 2]) * inv, __uint_as_float(t[i + 3]) * inv);
+          __nv_bfloat162 a2 = __floats2bfloat162_rn(__uint_as_float(t[i + 4]) * inv, __uint_as_float(t[i + 5]) * inv);
+          __nv_bfloat162 a3 = __floats2bfloat162_rn(__uint_as_float(t[i + 6]) * inv, __uint_as_float(t[i + 7]) * inv);
+          u.x = *reinterpret_cast<uint32_t*>(&a0);
+          u.y = *reinterpret_cast<uint32_t*>(&a1);
+          u.z = *reinterpret_cast<uint32_t*>(&a2);
+          u.w = *reinterpret_cast<uint32_t*>(&a3);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i) = u;
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int D>
+static int launch(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                  int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs, float scale,
+                  cudaStream_t st) {
+  using C = Cfg<D>;
+  CUtensorMap tq, tk, tv;
+  const uint32_t box[4] = {64, 128, 1, 1};
+  auto mk = [&](CUtensorMap* m, const void* p, int L, const long long* s3) {
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)L, (uint64_t)H, (uint64_t)B};
+    uint64_t str[4] = {2, (uint64_t)s3[2] * 2, (uint64_t)s3[1] * 2, (uint64_t)s3[0] * 2};
+    return make_tmap(m, p, 4, dims, str, box, 2, nullptr);
+  };
+  if (mk(&tq, q, Lq, qs)) return -20;
+  if (mk(&tk, k, Lk, ks)) return -21;
+  if (mk(&tv, v, Lk, vs)) return -22;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  dim3 grid((Lq + 255) / 256, B * H);
+  attention2_kernel<D><<<grid, 384, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
+                                                   Lk, scale * 1.4426950408889634f);
+  return (int)cudaGetLastError();
+}
+}  // namespace a2
+
+int attention2_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                    int H, int Lq, int Lk, int D, const long long* qs, const long long* ks, const long long* vs,
+                    float scale, cudaStream_t st) {
+  for (int i = 0; i < 3; ++i)
+    if (qs[i] % 8 || ks[i] % 8 || vs[i] % 8) return -10;
+  if (D == 128) return a2::launch<128>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  if (D == 64) return a2::launch<64>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  return -11;
+}
+
+}  // namespace pa
