@@ -149,12 +149,21 @@ _REAL_STDOUT = sys.stdout
 
 def emit(obj: dict):
     """The ONE JSON line goes to the real stdout; everything else (the reference's ``print`` chatter, our
-    logger) is routed to stderr by ``quiet_stdout`` so the line stays machine-readable."""
+    logger, NCCL's version banner written by C code to fd 1) is routed to stderr by ``quiet_stdout`` so the
+    line stays machine-readable."""
     _REAL_STDOUT.write(json.dumps(obj) + "\n")
     _REAL_STDOUT.flush()
 
 
 def quiet_stdout():
+    global _REAL_STDOUT
+    try:
+        sys.stdout.flush()
+        real_fd = os.dup(1)
+        os.dup2(2, 1)                       # fd 1 -> stderr for C-level writers
+        _REAL_STDOUT = os.fdopen(real_fd, "w")
+    except OSError:
+        pass
     sys.stdout = sys.stderr
 
 
