@@ -55,6 +55,20 @@ int num_sms() {
   return n[dev];
 }
 
+// Widest tile that (a) divides N without a ragged last tile where possible and (b) still yields at least one
+// tile per SM.  160 exists for the UNet channel counts (320 / 960 / 1920) that 256 and 128 tile badly.
+static int pick_bn(int N, int m_tiles) {
+  const int sms = num_sms();
+  const int cands[4] = {256, 160, 128, 64};
+  for (int c : cands) {
+    if (N % c) continue;
+    if (m_tiles * (N / c) >= sms) return c;
+  }
+  for (int c : cands)
+    if (N % c == 0) return c == 256 ? 128 : c;        // small problems: prefer more, smaller tiles
+  return 64;
+}
+
 template <int BN>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int tiles, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
@@ -85,12 +99,8 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
     } else if (p.N <= 64) {
       bn = 64;
     } else {
-      bn = 64;
-      const int cands[3] = {256, 128, 64};
-      for (int c : cands) {
-        if (p.N % c && p.N > c) continue;
-        if (m_tiles * ((p.N + c - 1) / c) >= num_sms()) { bn = c; break; }
-      }
+      bn = pick_bn(p.N, m_tiles);
+      if (p.mode == EPI_GEGLU && bn == 160) bn = 128;   // the GEGLU epilogue walks 64-column [a|g] groups
     }
   }
   if (p.mode == EPI_QKV_ROPE && bn < 128) return -12;
@@ -111,6 +121,7 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
   const int tiles = m_tiles * ((p.N + bn - 1) / bn);
   switch (bn) {
     case 256: return launch<256>(ta, tb, p, tiles, st);
+    case 160: return launch<160>(ta, tb, p, tiles, st);
     case 128: return launch<128>(ta, tb, p, tiles, st);
     case 64: return launch<64>(ta, tb, p, tiles, st);
   }
@@ -137,12 +148,7 @@ int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int ta
   p.batch = N;
   p.K = taps * p.conv_cblocks * 64;
   const int m_tiles = p.conv_tiles_w * p.conv_tiles_h * N;
-  int bn = 64;
-  const int cands[3] = {256, 128, 64};
-  for (int c : cands) {
-    if (p.N % c && p.N > c) continue;
-    if (m_tiles * ((p.N + c - 1) / c) >= num_sms() || c == 64) { bn = c; break; }
-  }
+  const int bn = pick_bn(p.N, m_tiles);
   CUtensorMap ta, tb;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
@@ -164,6 +170,7 @@ int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int ta
   const int tiles = m_tiles * ((p.N + bn - 1) / bn);
   switch (bn) {
     case 256: return launch<256>(ta, tb, p, tiles, st);
+    case 160: return launch<160>(ta, tb, p, tiles, st);
     case 128: return launch<128>(ta, tb, p, tiles, st);
     case 64: return launch<64>(ta, tb, p, tiles, st);
   }

@@ -43,11 +43,12 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128, BK = 64;
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 160 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t TMEM_COLS = 2 * BN;      // 128 / 256 / 512: powers of two >= 32
+  // two accumulator stages; the allocation must be a power of two >= 32 columns
+  static constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
   static constexpr int THREADS = 256;
 };
