@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..models import flux as flux_model
+from ..utils.log import nvtx_range
 
 
 def _bf16(t: torch.Tensor, device) -> torch.Tensor:
@@ -222,6 +223,7 @@ class FluxExecutor(nn.Module):
         n += 3
         # ---- double-stream blocks
         for i in range(self.n_double):
+          with nvtx_range(f"flux.double[{i}]"):
             for s, xs, xms, seq_off in (("img", Xi, XMi, Lt), ("txt", Xt, XMt, 0)):
                 k = ("d", i, s)
                 ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))

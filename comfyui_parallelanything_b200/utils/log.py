@@ -104,3 +104,24 @@ class Metrics:
         with open(path, "w") as f:
             for r in self.rows:
                 f.write(json.dumps(r) + "\n")
+
+
+class nvtx_range:
+    """``with nvtx_range("flux.double[3]"):`` — NVTX push/pop when ``PA_NVTX=1`` (for nsys/ncu timelines); a no-op
+    otherwise so the hot path pays nothing."""
+    enabled = os.environ.get("PA_NVTX", "0") not in ("0", "", "false")
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if self.enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
+        return False

@@ -664,3 +664,30 @@ def flux_executor_fp8():
     r["n_fp8_weights"] = sum(1 for k in ex8.W if k.endswith(".q"))
     r["ok"] = r["ok"] and r["n_fp8_weights"] > 0
     return r
+
+
+@check
+def pack_cache_roundtrip():
+    """Packed-weight checkpoint: save an fp8 FLUX executor, scramble it, restore it, same output."""
+    import os
+    import tempfile
+    from ..exec import pack_cache
+    from ..exec.flux_exec import FluxExecutor
+    from ..models import flux
+    p = flux.flux_tiny_params()
+    torch.manual_seed(5)
+    m = flux.Flux(p).to(device=_dev(), dtype=torch.bfloat16).eval()
+    ex = FluxExecutor(m, _dev(), fp8=True)
+    inp = flux.example_inputs(p, 1, 128, 128, txt_len=32, device=_dev(), dtype=torch.bfloat16)
+    before = ex(**inp).clone()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "flux_tiny.pa")
+        nbytes = pack_cache.save_packed(ex, path)
+        for k, v in ex.W.items():
+            if isinstance(v, torch.Tensor) and v.dtype == torch.bfloat16:
+                v.zero_()
+        broken = ex(**inp).clone()
+        meta = pack_cache.load_packed_into(ex, path)
+    after = ex(**inp)
+    ok = bool(torch.equal(before, after)) and not bool(torch.equal(before, broken)) and meta["fp8"] is True
+    return dict(name="pack_cache_roundtrip", ok=ok, bytes=nbytes, keys=meta["keys"])

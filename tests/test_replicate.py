@@ -89,3 +89,15 @@ def test_clear_caches_and_disable_flash():
     assert memory.disable_flash_xformers(m) >= 2
     assert m.double_blocks[0].img_attn.use_flash_attention is False and m.use_xformers is False
     assert memory.get_free_vram("cpu") == 0
+
+
+def test_ingest_state_dict_with_prefix(tmp_path):
+    from comfyui_parallelanything_b200.exec import pack_cache
+    src = flux.Flux(flux.flux_tiny_params())
+    sd = {"model.diffusion_model." + k: v for k, v in src.state_dict().items()}
+    path = tmp_path / "ckpt.pt"
+    torch.save(sd, path)
+    dst = flux.Flux(flux.flux_tiny_params())
+    res = pack_cache.ingest_state_dict(dst, str(path), prefix="model.diffusion_model.", strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    _same(src, dst)
