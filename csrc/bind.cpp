@@ -329,6 +329,13 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
   long long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
   long long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
   long long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  if (variant >= 21 && variant <= 23) {      // timing experiments of the ping-pong kernel (garbage results)
+    check(pa::attention2_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
+                               (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), variant - 20, qs, ks, vs,
+                               (float)scale, cur_stream()),
+          "attention2_debug");
+    return;
+  }
   auto fn = variant == 2 ? pa::attention2_bf16 : pa::attention_bf16;
   check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0), (int)q.size(0),
            (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale, cur_stream()),

@@ -66,6 +66,10 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
                     int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
                     const long long* v_strides, float scale, cudaStream_t st);
 
+int attention2_debug(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                     int H, int Lq, int Lk, int dbg, const long long* q_strides, const long long* k_strides,
+                     const long long* v_strides, float scale, cudaStream_t st);
+
 // GroupNorm (+ optional SiLU) on NHWC bf16
 int groupnorm_silu_nhwc_ws(const void* x, void* out, const void* gamma, const void* beta, float* workspace, int B,
                            int HW, int C, int groups, float eps, int apply_silu, cudaStream_t st);

@@ -82,7 +82,9 @@ struct Cfg {
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
 };
 
-template <int D>
+// DBG (timing experiments only, results are garbage for DBG != 0): 1 = skip the softmax math, 2 = skip the
+// TMEM read of S, 3 = skip both (pure barrier + MMA skeleton).
+template <int D, int DBG>
 __global__ void __launch_bounds__(384, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
@@ -226,11 +228,31 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
         uint32_t(&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
         uint32_t(&c3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
-        ptx::tmem_ld_32x32b_x32(s_addr, c0);
-        ptx::tmem_ld_32x32b_x32(s_addr + 32, c1);
-        ptx::tmem_ld_32x32b_x32(s_addr + 64, c2);
-        ptx::tmem_ld_32x32b_x32(s_addr + 96, c3);
-        ptx::tmem_ld_wait();
+        if (DBG & 2) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i) sv[i] = 0x3c000000u + i + j;
+        } else {
+          ptx::tmem_ld_32x32b_x32(s_addr, c0);
+          ptx::tmem_ld_32x32b_x32(s_addr + 32, c1);
+          ptx::tmem_ld_32x32b_x32(s_addr + 64, c2);
+          ptx::tmem_ld_32x32b_x32(s_addr + 96, c3);
+          ptx::tmem_ld_wait();
+        }
+      }
+      if (DBG & 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = (sv[c * 32 + 2 * i] >> 16) | (sv[c * 32 + 2 * i + 1] & 0xffff0000u);
+          ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);
+        }
+        ptx::tmem_st_wait();
+        l = 1.f;
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+        continue;
       }
       const int kv_left = Lk - j * BN;
       if (kv_left < BN) {
@@ -337,7 +359,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int D>
+template <int D, int DBG>
 static int launch(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                   int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs, float scale,
                   cudaStream_t st) {
@@ -356,12 +378,13 @@ static int launch(const void* q, const void* k, const void* v, void* out, long l
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
   dim3 grid((Lq + 255) / 256, B * H);
-  attention2_kernel<D><<<grid, 384, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
+  attention2_kernel<D, DBG><<<grid, 384, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
                                                    Lk, scale * 1.4426950408889634f);
   return (int)cudaGetLastError();
 }
@@ -372,8 +395,18 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
                     float scale, cudaStream_t st) {
   for (int i = 0; i < 3; ++i)
     if (qs[i] % 8 || ks[i] % 8 || vs[i] % 8) return -10;
-  if (D == 128) return a2::launch<128>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
-  if (D == 64) return a2::launch<64>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  if (D == 128) return a2::launch<128, 0>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  if (D == 64) return a2::launch<64, 0>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  return -11;
+}
+
+// timing experiments (D = 128 only): dbg 1..3, see attention2_kernel
+int attention2_debug(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                     int H, int Lq, int Lk, int dbg, const long long* qs, const long long* ks, const long long* vs,
+                     float scale, cudaStream_t st) {
+  if (dbg == 1) return a2::launch<128, 1>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  if (dbg == 2) return a2::launch<128, 2>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  if (dbg == 3) return a2::launch<128, 3>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
   return -11;
 }
 
