@@ -105,6 +105,8 @@ def main() -> int:
             torch.set_default_dtype(torch.bfloat16)
             torch.manual_seed(1234)
             model = unet.UNetModel(**cfg).to(device=lead, dtype=torch.bfloat16).eval()
+            torch.nn.Linear.reset_parameters = lambda self: None      # clones are overwritten anyway (see bench.py)
+            torch.nn.Conv2d.reset_parameters = lambda self: None
             chain = None
             for i in range(a.gpus):
                 chain = ref.ParallelDevice().add_device(f"cuda:{i}", float(pcts[i]), chain)[0]

@@ -27,6 +27,52 @@ elif which == "gemm_gelu":
     out = torch.empty(M, N, **bf)
     for _ in range(4):
         ops.gemm(a, w, "gelu", out=out, bias=b)
+elif which == "gemm_sdxl":    # SDXL transformer to_out / proj: small K, residual epilogue
+    M, K, N = 16384, 1280, 1280
+    a, w, b = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.03, torch.randn(N, **bf)
+    res = torch.randn(M, N, **bf)
+    out = torch.empty(M, N, **bf)
+    for _ in range(4):
+        ops.gemm(a, w, "res", out=out, bias=b, residual=res)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.gemm(a, w, "res", out=out, bias=b, residual=res)
+    e1.record()
+    torch.cuda.synchronize()
+    print("gemm_sdxl res ms", e0.elapsed_time(e1) / 20, "TFLOP/s", 2.0 * M * N * K / (e0.elapsed_time(e1) / 20) / 1e9)
+    e0.record()
+    for _ in range(20):
+        ops.gemm(a, w, "bias", out=out, bias=b)
+    e1.record()
+    torch.cuda.synchronize()
+    print("gemm_sdxl bias ms", e0.elapsed_time(e1) / 20, "TFLOP/s", 2.0 * M * N * K / (e0.elapsed_time(e1) / 20) / 1e9)
+elif which == "attn2":
+    q, k, v = (torch.randn(1, 24, 4608, 128, **bf) for _ in range(3))
+    for _ in range(4):
+        ops.attention(q, k, v, variant=2)
+elif which == "mxfp8":
+    M, K, N = 9216, 3072, 9216
+    a, w = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.02
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, sfb = ops.quantize_mxfp8(w, 224)
+    out = torch.empty(M, N, **bf)
+    for _ in range(4):
+        ops.gemm_fp8(aq, sfa, wq, sfb, "bias", 224, out=out)
+elif which == "scatter":
+    C_ = ops.require()
+    x = torch.randn(2, 16, 128, 128, **bf)
+    w, b = torch.randn(3072, 64, **bf) * 0.1, torch.randn(3072, **bf)
+    t = torch.rand(2, **bf)
+    X = torch.empty(2, 4608, 3072, **bf)
+    te, ge = torch.empty(2, 256, **bf), torch.empty(2, 256, **bf)
+    for _ in range(4):
+        C_.scatter_patch_embed(w, b, x.data_ptr(), t.data_ptr(), t.data_ptr(), te, ge, None, X[:, 512:], 16, 128, 128, 1000.0)
+elif which == "conv":
+    x = torch.randn(4, 128, 128, 320, **bf)
+    wt = ops.pack_conv_weight(torch.randn(320, 320, 3, 3, **bf) * 0.02)
+    for _ in range(4):
+        ops.conv2d_nhwc(x, wt, 9, 1, "bias")
 elif which == "attn":
     q, k, v = (torch.randn(1, 24, 4608, 128, **bf) for _ in range(3))
     for _ in range(4):
