@@ -329,7 +329,7 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
   long long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
   long long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
   long long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
-  if (variant >= 21 && variant <= 23) {      // timing experiments of the ping-pong kernel (garbage results)
+  if (variant >= 21 && variant <= 120) {      // timing experiments of the ping-pong kernel (garbage results)
     check(pa::attention2_debug(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),
                                (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), variant - 20, qs, ks, vs,
                                (float)scale, cur_stream()),
@@ -340,6 +340,12 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
   check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0), (int)q.size(0),
            (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale, cur_stream()),
         "attention");
+}
+
+static Tensor attention2_trace() {
+  Tensor t = at::zeros({5, 64, 8}, at::TensorOptions().dtype(at::kLong));
+  check(pa::attention2_trace_read(reinterpret_cast<long long*>(t.data_ptr<int64_t>())), "attention2_trace_read");
+  return t;
 }
 
 static void groupnorm_silu(Tensor x, Tensor out, Tensor gamma, Tensor beta, int groups, double eps, bool silu) {
@@ -402,6 +408,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("add", &add_);
   m.def("attention", &attention, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("scale"),
         py::arg("variant") = 1);
+  m.def("attention2_trace", &attention2_trace);
   m.def("groupnorm_silu", &groupnorm_silu);
   m.def("cfg_euler_store", &cfg_euler_store);
   m.def("signal_flags", &signal_flags);

@@ -42,6 +42,7 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int m_per = (p.Li + BM - 1) / BM;
   const int b = blockIdx.x / m_per;
   const int tok0 = (blockIdx.x - b * m_per) * BM;
@@ -67,34 +68,42 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      for (int nt = 0; nt < num_n; ++nt) {
-        const int s = nt % WSTAGES;
-        const uint32_t ph = (nt / WSTAGES) & 1;
-        ptx::mbar_wait(&w_empty[s], ph ^ 1);
+  if (warp_u == 0) {
+    // weight-tile producer (whole warp on uniform values, one elected lane issues; see gemm_tcgen05.cuh)
+    const bool leader = ptx::elect_one();
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    for (int nt = 0; nt < num_n; ++nt) {
+      const int s = nt % WSTAGES;
+      const uint32_t ph = (nt / WSTAGES) & 1;
+      ptx::mbar_wait(&w_empty[s], ph ^ 1);
+      if (leader) {
         ptx::mbar_arrive_expect_tx(&w_full[s], W_BYTES);
-        ptx::tma_load_2d(smem + OFF_W + s * W_BYTES, &tmW, &w_full[s], 0, nt * BN);
+        ptx::tma_load_2d_s(smem_u + OFF_W + s * W_BYTES, &tmW, &w_full[s], 0, nt * BN);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC = ptx::make_idesc_f16(BM, BN);
-      ptx::mbar_wait(a_full, 0);
+    __syncwarp();
+  } else if (warp_u == 1) {
+    constexpr uint32_t IDESC = ptx::make_idesc_f16(BM, BN);
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    ptx::mbar_wait(a_full, 0);
+    ptx::tc_fence_after();
+    const uint64_t adesc = ptx::make_desc_kmajor_sw128(smem_u);
+    for (int nt = 0; nt < num_n; ++nt) {
+      const int s = nt % WSTAGES, acc = nt & 1;
+      ptx::mbar_wait(&w_full[s], (nt / WSTAGES) & 1);
+      ptx::mbar_wait(&tempty[acc], ((nt >> 1) & 1) ^ 1);
       ptx::tc_fence_after();
-      const uint64_t adesc = ptx::make_desc_kmajor_sw128(ptx::smem_u32(smem));
-      for (int nt = 0; nt < num_n; ++nt) {
-        const int s = nt % WSTAGES, acc = nt & 1;
-        ptx::mbar_wait(&w_full[s], (nt / WSTAGES) & 1);
-        ptx::mbar_wait(&tempty[acc], ((nt >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint64_t bdesc = ptx::make_desc_kmajor_sw128(ptx::smem_u32(smem + OFF_W + s * W_BYTES));
+      if (leader) {
+        const uint64_t bdesc = ptx::make_desc_kmajor_sw128(smem_u + OFF_W + s * W_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem + acc * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, k != 0);
+        for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_u + acc * BN, adesc + 2 * k, bdesc + 2 * k, IDESC, k != 0);
         ptx::tc_commit(&w_empty[s]);
         ptx::tc_commit(&tfull[acc]);
       }
     }
+    __syncwarp();
   } else if (warp == 3) {
     // timestep / guidance sinusoidal embeddings of the shard (values read from the lead GPU)
     if (blockIdx.x == 0) {

@@ -61,6 +61,7 @@ int attention_bf16(const void* q, const void* k, const void* v, void* out, long 
                    int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
                    const long long* v_strides, float scale, cudaStream_t st);
 
+int attention2_trace_read(long long* host);
 // ping-pong variant (two query tiles per CTA, csrc/kernels/attention2.cu); same contract
 int attention2_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                     int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,

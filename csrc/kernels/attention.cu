@@ -127,6 +127,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int q0 = blockIdx.x * BM;
   const int bh = blockIdx.y;
   const int n_kv = (Lk + BN - 1) / BN;
@@ -161,70 +162,83 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      const int hb = bh / H, hh = bh - hb * H;
+  // Producer and MMA roles run as whole warps on warp-uniform values, one elected lane issues (inside a `lane == 0`
+  // branch ptxas wraps every UTMALDG / UTCHMMA in an ELECT + R2UR.BROADCAST waterfall loop, ~90 cycles per MMA).
+  if (warp_u == 0) {
+    const bool leader = ptx::elect_one();
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    const int hb = bh / H, hh = bh - hb * H;
+    if (leader) {
       ptx::mbar_arrive_expect_tx(q_full, TILE_BYTES);
 #pragma unroll
       for (int sl = 0; sl < D / 64; ++sl)
-        ptx::tma_load_4d(smem + OFF_Q + sl * SLICE_BYTES, &tmQ, q_full, sl * 64, q0, hh, hb);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(&k_empty[s], ph ^ 1);
+        ptx::tma_load_4d_s(smem_u + OFF_Q + sl * SLICE_BYTES, &tmQ, q_full, sl * 64, q0, hh, hb);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      ptx::mbar_wait(&k_empty[s], ph ^ 1);
+      if (leader) {
         ptx::mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
 #pragma unroll
         for (int sl = 0; sl < D / 64; ++sl)
-          ptx::tma_load_4d(smem + OFF_K + s * TILE_BYTES + sl * SLICE_BYTES, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
-        ptx::mbar_wait(&v_empty[s], ph ^ 1);
+          ptx::tma_load_4d_s(smem_u + OFF_K + s * TILE_BYTES + sl * SLICE_BYTES, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
+      }
+      ptx::mbar_wait(&v_empty[s], ph ^ 1);
+      if (leader) {
         ptx::mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
 #pragma unroll
         for (int sl = 0; sl < D / 64; ++sl)
-          ptx::tma_load_4d(smem + OFF_V + s * TILE_BYTES + sl * SLICE_BYTES, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
+          ptx::tma_load_4d_s(smem_u + OFF_V + s * TILE_BYTES + sl * SLICE_BYTES, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
-      constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);     // B (= V) is MN-major, N = D
-      const uint32_t q_addr = ptx::smem_u32(smem + OFF_Q);
-      auto issue_qk = [&](int i) {
-        const int s = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
-        ptx::mbar_wait(&k_full[s], ph);
-        ptx::mbar_wait(&s_empty[s], ph ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t k_addr = ptx::smem_u32(smem + OFF_K + s * TILE_BYTES);
+    __syncwarp();
+  } else if (warp_u == 1) {
+    constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
+    constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);     // B (= V) is MN-major, N = D
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    const uint64_t qd = ptx::make_desc_kmajor_sw128(smem_u + OFF_Q);
+    auto issue_qk = [&](int i) {
+      const int s = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      ptx::mbar_wait(&k_full[s], ph);
+      ptx::mbar_wait(&s_empty[s], ph ^ 1);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint64_t kd = ptx::make_desc_kmajor_sw128(smem_u + OFF_K + s * TILE_BYTES);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * SLICE_BYTES + (kk & 3) * 32;
-          ptx::mma_f16_ss(tmem + s * 128, ptx::make_desc_kmajor_sw128(q_addr + off),
-                          ptx::make_desc_kmajor_sw128(k_addr + off), IDESC_QK, kk != 0);
+          const uint32_t off = ((kk >> 2) * SLICE_BYTES + (kk & 3) * 32) >> 4;   // descriptor address unit = 16 B
+          ptx::mma_f16_ss(tmem_u + s * 128, qd + off, kd + off, IDESC_QK, kk != 0);
         }
         ptx::tc_commit(&k_empty[s]);
         ptx::tc_commit(&s_full[s]);
-      };
-      ptx::mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(&p_full[s], ph);
-        ptx::mbar_wait(&v_full[s], ph);
-        ptx::tc_fence_after();
-        const uint32_t v_addr = ptx::smem_u32(smem + OFF_V + s * TILE_BYTES);
+      }
+    };
+    ptx::mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      ptx::mbar_wait(&p_full[s], ph);
+      ptx::mbar_wait(&v_full[s], ph);
+      ptx::tc_fence_after();
+      if (leader) {
+        const uint64_t vd = ptx::make_desc_mnmajor_sw128(smem_u + OFF_V + s * TILE_BYTES, SLICE_BYTES, 1024);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
-          // A = P_j from tensor memory: 16 keys = 8 packed 32-bit columns per MMA
-          const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE_BYTES, 1024);
-          ptx::mma_f16_ts(tmem + 256, tmem + TMEM_P + s * 64 + kk * 8, b, IDESC_PV, (j | kk) != 0);
+          // A = P_j from tensor memory: 16 keys = 8 packed 32-bit columns per MMA; V advances 16 rows x 128 B
+          ptx::mma_f16_ts(tmem_u + 256, tmem_u + TMEM_P + s * 64 + kk * 8, vd + kk * 128, IDESC_PV, (j | kk) != 0);
         }
         ptx::tc_commit(&v_empty[s]);
         ptx::tc_commit(&p_empty[s]);
         ptx::tc_commit(&o_full[0]);          // phase j & 1: "O includes tiles 0..j"
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int q4 = warp & 3;
     const int half = (warp - 4) >> 2;                  // 0: key columns 0..63 of each tile, 1: columns 64..127

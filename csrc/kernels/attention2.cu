@@ -70,6 +70,14 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, flo
   r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xr1) << 23));
 }
 
+// timeline capture for DBG & 64: [role 0..4][kv tile 0..63][slot 0..7] clock64 stamps of CTA (1, 1)
+__device__ long long g_trace[5 * 64 * 8];
+#define PA_TR(role, j, slot)                                                          \
+  do {                                                                                \
+    if ((DBG & 64) && blockIdx.x == 1 && blockIdx.y == 1 && (j) < 64)                 \
+      g_trace[((role) * 64 + (j)) * 8 + (slot)] = clock64();                          \
+  } while (0)
+
 template <int D>
 struct Cfg {
   static constexpr int BN = 128;
@@ -82,8 +90,9 @@ struct Cfg {
   static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
 };
 
-// DBG (timing experiments only, results are garbage for DBG != 0): 1 = skip the softmax math, 2 = skip the
-// TMEM read of S, 3 = skip both (pure barrier + MMA skeleton).
+// DBG (timing experiments only, results are garbage for DBG != 0), bit mask: 1 = skip the softmax math, 2 = skip the
+// TMEM read of S, 4 = Q.K^T issues one MMA instead of D/16, 8 = P.V issues one MMA instead of 8, 16 = P.V reads its
+// A operand from shared memory (SS form) instead of tensor memory.
 template <int D, int DBG>
 __global__ void __launch_bounds__(384, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -106,6 +115,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int q0 = blockIdx.x * 256;
   const int bh = blockIdx.y;
   const int n_kv = (Lk + BN - 1) / BN;
@@ -137,75 +147,111 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
   if (warp < 4) {
     ptx::setmaxnreg_dec<56>();
-    if (warp == 0 && lane == 0) {
-      // ===================== TMA producer =====================
+    if (warp_u == 0) {
+      // ===================== TMA producer (whole warp, one elected lane issues) =====================
+      const bool leader = ptx::elect_one();
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
       const int hb = bh / H, hh = bh - hb * H;
-      ptx::mbar_arrive_expect_tx(q_full, 2 * TILE);
+      if (leader) {
+        ptx::mbar_arrive_expect_tx(q_full, 2 * TILE);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int sl = 0; sl < D / 64; ++sl)
-          ptx::tma_load_4d(smem + C::OFF_Q + t * TILE + sl * SLICE, &tmQ, q_full, sl * 64, q0 + t * 128, hh, hb);
+          for (int sl = 0; sl < D / 64; ++sl)
+            ptx::tma_load_4d_s(smem_base + C::OFF_Q + t * TILE + sl * SLICE, &tmQ, q_full, sl * 64, q0 + t * 128, hh, hb);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
         ptx::mbar_wait(&k_empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&k_full[s], TILE);
+        if (leader) {
+          PA_TR(4, j, 0);
+          ptx::mbar_arrive_expect_tx(&k_full[s], TILE);
 #pragma unroll
-        for (int sl = 0; sl < D / 64; ++sl)
-          ptx::tma_load_4d(smem + C::OFF_K + s * TILE + sl * SLICE, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
+          for (int sl = 0; sl < D / 64; ++sl)
+            ptx::tma_load_4d_s(smem_base + C::OFF_K + s * TILE + sl * SLICE, &tmK, &k_full[s], sl * 64, j * BN, hh, hb);
+        }
         ptx::mbar_wait(&v_empty[s], ph ^ 1);
-        ptx::mbar_arrive_expect_tx(&v_full[s], TILE);
+        if (leader) {
+          PA_TR(4, j, 1);
+          ptx::mbar_arrive_expect_tx(&v_full[s], TILE);
 #pragma unroll
-        for (int sl = 0; sl < D / 64; ++sl)
-          ptx::tma_load_4d(smem + C::OFF_V + s * TILE + sl * SLICE, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
+          for (int sl = 0; sl < D / 64; ++sl)
+            ptx::tma_load_4d_s(smem_base + C::OFF_V + s * TILE + sl * SLICE, &tmV, &v_full[s], sl * 64, j * BN, hh, hb);
+        }
       }
-    } else if (warp == 1 && lane == 0) {
+      __syncwarp();
+    } else if (warp_u == 1) {
       // ===================== MMA issuer =====================
+      // The whole warp runs this role with warp-uniform values and one elected lane issues the tcgen05 ops: inside a
+      // `lane == 0` branch ptxas cannot prove the descriptors uniform and wraps EVERY UTCHMMA in an
+      // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~90 cycles per MMA, more than the 64 cycles a 128x128x16
+      // MMA executes) - measured with the PA_TR timeline: the issue thread, not the tensor pipe, set the period.
       constexpr uint32_t IDESC_QK = ptx::make_idesc_f16(128, 128, 1, 0, 0);
       constexpr uint32_t IDESC_PV = ptx::make_idesc_f16(128, D, 1, 0, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint32_t smem_base = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+      const bool leader = ptx::elect_one();
       auto qk = [&](int x, int i) {            // S_X = Q_X K_i^T
-        const uint32_t q_addr = ptx::smem_u32(smem + C::OFF_Q + x * TILE);
-        const uint32_t k_addr = ptx::smem_u32(smem + C::OFF_K + (i & 1) * TILE);
+        if (leader) {
+          const uint64_t qd = ptx::make_desc_kmajor_sw128(smem_base + C::OFF_Q + x * TILE);
+          const uint64_t kd = ptx::make_desc_kmajor_sw128(smem_base + C::OFF_K + (i & 1) * TILE);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * SLICE + (kk & 3) * 32;
-          ptx::mma_f16_ss(tmem + x * 128, ptx::make_desc_kmajor_sw128(q_addr + off),
-                          ptx::make_desc_kmajor_sw128(k_addr + off), IDESC_QK, kk != 0);
+          for (int kk = 0; kk < ((DBG & 4) ? 1 : D / 16); ++kk) {
+            const uint32_t off = ((kk >> 2) * SLICE + (kk & 3) * 32) >> 4;     // descriptor address field: bytes / 16
+            ptx::mma_f16_ss(tmem_u + x * 128, qd + off, kd + off, IDESC_QK, kk != 0);
+          }
+          ptx::tc_commit(&s_full[x]);
         }
-        ptx::tc_commit(&s_full[x]);
       };
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(&k_full[0], 0);
       ptx::tc_fence_after();
       qk(0, 0);
       qk(1, 0);
-      ptx::tc_commit(&k_empty[0]);
+      if (leader) ptx::tc_commit(&k_empty[0]);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1;
         ptx::mbar_wait(&v_full[st], (j >> 1) & 1);
-        const uint32_t v_addr = ptx::smem_u32(smem + C::OFF_V + st * TILE);
+        if (leader) PA_TR(0, j, 4);
+        const uint64_t vd = ptx::make_desc_mnmajor_sw128(smem_base + C::OFF_V + st * TILE, SLICE, 1024);
 #pragma unroll 1
         for (int x = 0; x < 2; ++x) {
           ptx::mbar_wait(&p_full[x], j & 1);
           ptx::tc_fence_after();
+          if (leader) {
+            PA_TR(x, j, 0);
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t b = ptx::make_desc_mnmajor_sw128(v_addr + kk * 2048, SLICE, 1024);
-            ptx::mma_f16_ts(tmem + 256 + x * 128, tmem + x * 128 + kk * 8, b, IDESC_PV, (j | kk) != 0);
+            for (int kk = 0; kk < ((DBG & 8) ? 1 : 8); ++kk) {
+              if (DBG & 16) {
+                const uint32_t off = ((kk >> 2) * SLICE + (kk & 3) * 32) >> 4;
+                ptx::mma_f16_ss(tmem_u + 256 + x * 128,
+                                ptx::make_desc_kmajor_sw128(smem_base + C::OFF_Q + x * TILE) + off, vd + kk * 128, IDESC_PV,
+                                (j | kk) != 0);
+              } else {
+                ptx::mma_f16_ts(tmem_u + 256 + x * 128, tmem_u + x * 128 + kk * 8, vd + kk * 128, IDESC_PV,
+                                (j | kk) != 0);
+              }
+            }
+            ptx::tc_commit(&o_full[x]);
+            if (x == 1) ptx::tc_commit(&v_empty[st]);
+            PA_TR(x, j, 1);
           }
-          ptx::tc_commit(&o_full[x]);
-          if (x == 1) ptx::tc_commit(&v_empty[st]);
           if (j + 1 < n_kv) {
             if (x == 0) {
               ptx::mbar_wait(&k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
               ptx::tc_fence_after();
             }
+            if (leader) PA_TR(x, j, 2);
             qk(x, j + 1);                      // overwrites S_X / P_X: ordered after P_X.V in the tensor pipe
-            if (x == 1) ptx::tc_commit(&k_empty[(j + 1) & 1]);
+            if (leader) {
+              if (x == 1) ptx::tc_commit(&k_empty[(j + 1) & 1]);
+              PA_TR(x, j, 3);
+            }
           }
         }
       }
+      __syncwarp();
     }
   } else {
     ptx::setmaxnreg_inc<208>();
@@ -221,6 +267,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     for (int j = 0; j < n_kv; ++j) {
       ptx::mbar_wait(&s_full[x], j & 1);
+      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 0);
       ptx::tc_fence_after();
       uint32_t sv[128];
       {
@@ -239,6 +286,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ptx::tmem_ld_wait();
         }
       }
+      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 1);
       if (DBG & 1) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -252,6 +300,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+        if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 4);
         continue;
       }
       const int kv_left = Lk - j * BN;
@@ -289,6 +338,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ptx::tmem_st_wait();
         }
       }
+      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 2);
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
       unsigned long long sum2 = pack2(0.f, 0.f);
@@ -313,6 +363,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);    // P_X: keys 32c..32c+31 -> packed columns 16c..16c+15
       }
+      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 3);
       ptx::tmem_st_wait();
       float s0, s1;
       unpack2(sum2, s0, s1);
@@ -320,6 +371,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 4);
     }
 
     ptx::mbar_wait(&o_full[x], (n_kv - 1) & 1);
@@ -404,10 +456,17 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
 int attention2_debug(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                      int H, int Lq, int Lk, int dbg, const long long* qs, const long long* ks, const long long* vs,
                      float scale, cudaStream_t st) {
-  if (dbg == 1) return a2::launch<128, 1>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
-  if (dbg == 2) return a2::launch<128, 2>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
-  if (dbg == 3) return a2::launch<128, 3>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+#define PA_A2_DBG(N) \
+  if (dbg == N) return a2::launch<128, N>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  PA_A2_DBG(1) PA_A2_DBG(2) PA_A2_DBG(3) PA_A2_DBG(7) PA_A2_DBG(11) PA_A2_DBG(15) PA_A2_DBG(19) PA_A2_DBG(16)
+  PA_A2_DBG(64) PA_A2_DBG(67) PA_A2_DBG(79)
+#undef PA_A2_DBG
   return -11;
+}
+
+// copies the DBG & 64 timeline (5 x 64 x 8 clock64 stamps) of the last traced launch to `host`
+int attention2_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, a2::g_trace, sizeof(long long) * 5 * 64 * 8);
 }
 
 }  // namespace pa

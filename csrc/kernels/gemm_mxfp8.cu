@@ -38,9 +38,9 @@ struct Mx8Cfg {
   static_assert(ACC_COLS + 4 + 4 * NCHUNK <= 512, "TMEM budget");
 };
 
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   ptx::smem_u32(smem_dst)),
+                   smem_dst),
                "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
                : "memory");
 }
@@ -68,6 +68,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -108,47 +109,55 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     nt = r / gsz;
   };
 
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int mt, nt;
-        decode(t, mt, nt);
-        const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
-        const uint8_t* sfa_t = sfa + static_cast<long long>(mt) * num_k * 512;
-        const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * NCHUNK * num_k * 512;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
+  // Producer and MMA roles run as whole warps on warp-uniform values with one elected lane issuing (inside a
+  // `lane == 0` branch ptxas wraps every UTMALDG / UTCQMMA in an ELECT + R2UR.BROADCAST waterfall loop).
+  if (warp_u == 0) {
+    const bool leader = ptx::elect_one();
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mt, nt;
+      decode(t, mt, nt);
+      const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
+      const uint8_t* sfa_t = sfa + static_cast<long long>(mt) * num_k * 512;
+      const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * NCHUNK * num_k * 512;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        if (leader) {
           ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_STRIDE;
-          ptx::tma_load_3d(sa, &tmA, &full[stage], kb * BK, mrow, b);
-          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
+          const uint32_t sa = smem_u + stage * Cfg::STAGE_STRIDE;
+          ptx::tma_load_3d_s(sa, &tmA, &full[stage], kb * BK, mrow, b);
+          ptx::tma_load_2d_s(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
           bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES, sfa_t + static_cast<long long>(kb) * 512, 512, &full[stage]);
 #pragma unroll
           for (int j = 0; j < NCHUNK; ++j)
             bulk_load_1d(sa + Cfg::A_BYTES + Cfg::B_BYTES + 512 + j * 512,
                          sfb_t + (static_cast<long long>(j) * num_k + kb) * 512, 512, &full[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      const uint32_t sfa_t = tmem_base + Cfg::SF_COL, sfb_t = tmem_base + Cfg::SF_COL + 4;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = ACC == 2 ? (it & 1) : 0;
-        const uint32_t acc_phase = ACC == 2 ? ((it >> 1) & 1) : (it & 1);
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+    __syncwarp();
+  } else if (warp_u == 1) {
+    const bool leader = ptx::elect_one();
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    const uint32_t sfa_t = tmem_u + Cfg::SF_COL, sfb_t = tmem_u + Cfg::SF_COL + 4;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = ACC == 2 ? (it & 1) : 0;
+      const uint32_t acc_phase = ACC == 2 ? ((it >> 1) & 1) : (it & 1);
+      ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_u + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_STRIDE);
+        if (leader) {
+          const uint32_t sa = smem_u + stage * Cfg::STAGE_STRIDE;
           // scale factors of this K-block: smem -> TMEM (ordered with the MMAs in the tensor-core pipe)
           ptx::tmem_cp_32x128b_warpx4(sfa_t, make_sf_desc(sa + Cfg::A_BYTES + Cfg::B_BYTES));
 #pragma unroll
@@ -163,10 +172,11 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           ptx::tc_commit(&empty[stage]);
           if (kb == num_k - 1) ptx::tc_commit(&tfull[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     const int q4 = warp & 3;
     const int r_in_tile = q4 * 32 + lane;

@@ -296,6 +296,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -338,54 +339,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     nt = r / gsz;
   };
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int mt, nt;
-        decode(t, mt, nt);
-        const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
-        int h0 = 0, w0 = 0;
-        if (conv) {
-          const int t_in = mt - b * m_per_batch;
-          const int ti_h = t_in / p.conv_tiles_w;
-          h0 = ti_h * p.conv_th * p.conv_stride - p.conv_pad;
-          w0 = (t_in - ti_h * p.conv_tiles_w) * p.conv_tw * p.conv_stride - p.conv_pad;
-        }
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&empty[stage], phase ^ 1);
+  if (warp_u == 0) {
+    // ===================== TMA producer (whole warp, one elected lane issues; see the MMA role) =====================
+    const bool leader = ptx::elect_one();
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mt, nt;
+      decode(t, mt, nt);
+      const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
+      int h0 = 0, w0 = 0;
+      if (conv) {
+        const int t_in = mt - b * m_per_batch;
+        const int ti_h = t_in / p.conv_tiles_w;
+        h0 = ti_h * p.conv_th * p.conv_stride - p.conv_pad;
+        w0 = (t_in - ti_h * p.conv_tiles_w) * p.conv_tw * p.conv_stride - p.conv_pad;
+      }
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        if (leader) {
           ptx::mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          const uint32_t sa = smem_u + stage * Cfg::STAGE_BYTES;
           if (conv) {
             const int tap = kb / p.conv_cblocks, cb = kb - tap * p.conv_cblocks;
             const int kh = p.conv_taps == 9 ? tap / 3 : 0, kw = p.conv_taps == 9 ? tap - kh * 3 : 0;
-            ptx::tma_load_4d(sa, &tmA, &full[stage], cb * BK, w0 + kw, h0 + kh, b);
+            ptx::tma_load_4d_s(sa, &tmA, &full[stage], cb * BK, w0 + kw, h0 + kh, b);
           } else {
-            ptx::tma_load_3d(sa, &tmA, &full[stage], kb * BK, mrow, b);
+            ptx::tma_load_3d_s(sa, &tmA, &full[stage], kb * BK, mrow, b);
           }
-          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          ptx::tma_load_2d_s(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nt * BN);
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+    __syncwarp();
+  } else if (warp_u == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // Whole warp, warp-uniform values, one elected lane issues: inside a `lane == 0` branch ptxas wraps every
+    // UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~90 cycles per MMA - slower than a 128x128x16 MMA
+    // executes); with uniform descriptors the MMAs issue back to back from uniform registers.
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+    const bool leader = ptx::elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_u + acc * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        if (leader) {
+          const uint32_t sa = smem_u + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);
           const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES);
 #pragma unroll
@@ -395,10 +405,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           ptx::tc_commit(&empty[stage]);
           if (kb == num_k - 1) ptx::tc_commit(&tfull[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue (4 warps, thread == accumulator row) =====================
     const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read

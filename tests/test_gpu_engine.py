@@ -87,3 +87,15 @@ def test_multi_gpu_weighted_split_and_generic_module():
     assert torch.allclose(got, want, atol=1e-5)
     assert m._parallel_engine.metrics.rows[-1]["sizes"] == [7, 3]
     pa.cleanup_parallel_model(m)
+
+
+def test_stranded_model_is_moved_back_to_its_load_device():
+    """C21 (ADP:932-961): weights left on the CPU by an earlier run while the patcher says cuda:0."""
+    from comfyui_parallelanything_b200 import nodes
+
+    class Patcher:
+        load_device = torch.device("cuda:0")
+
+    m = nn.Sequential(nn.Linear(8, 8), nn.Linear(8, 8))
+    nodes._repair_stranded(Patcher(), m)
+    assert all(p.device == torch.device("cuda:0") for p in m.parameters())

@@ -46,3 +46,18 @@ def test_passthrough_on_bad_input():
     assert node.setup_parallel(m, []) == (m,)
     out, = node.setup_parallel(m, [{"device": "bogus:9", "percentage": 100, "weight": 1.0}])
     assert out is m and not getattr(m, "_true_parallel_active", False)
+
+
+def test_repair_stranded_is_a_noop_without_a_cuda_home():
+    """C21 (ADP:932-961): only a model that ComfyUI believes lives on a CUDA device is moved back."""
+    from comfyui_parallelanything_b200 import nodes
+
+    class Patcher:
+        load_device = torch.device("cpu")
+
+    m = nn.Linear(4, 4)
+    nodes._repair_stranded(Patcher(), m)
+    assert m.weight.device.type == "cpu"
+    Patcher.load_device = None
+    nodes._repair_stranded(Patcher(), m)            # no load_device and no comfy.model_management: leave it alone
+    assert m.weight.device.type == "cpu"

@@ -19,6 +19,9 @@ def main() -> int:
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    family = sys.argv[1] if len(sys.argv) > 1 else "flux"
+    if family != "flux":
+        return other_family(family, rank, world, dev)
     from comfyui_parallelanything_b200.exec.flux_exec import FluxExecutor
     from comfyui_parallelanything_b200.models import flux
     from comfyui_parallelanything_b200.parallel.spmd import SpmdFluxEngine
@@ -51,6 +54,57 @@ def main() -> int:
     if rank == 0:
         ok = all(v["mean_rel"] < 5e-3 for v in res.values())
         print("PA_SPMD " + json.dumps(dict(world=world, ok=ok, results=res)), flush=True)
+    dist.destroy_process_group()
+    return 0
+
+
+def other_family(family, rank, world, dev) -> int:
+    """Same comparison for the SDXL-class UNet (``unet``) and the WAN video DiT (``wan``) engines."""
+    import torch
+    import torch.distributed as dist
+    from comfyui_parallelanything_b200.parallel import spmd
+    B = 5 if world == 2 else 2 * world + 1
+    sig = torch.tensor([[1.0 - 0.1 * i, 0.8 - 0.1 * i] for i in range(B)], device=dev)
+    if family == "unet":
+        from comfyui_parallelanything_b200.exec.unet_exec import UNetExecutor
+        from comfyui_parallelanything_b200.models import unet
+        cfg = unet.mini_sdxl_config()
+        torch.manual_seed(3)
+        ex = UNetExecutor(unet.UNetModel(**cfg).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        inp = unet.example_inputs(cfg, B, 256, 384, ctx_len=77, device=dev, dtype=torch.bfloat16)
+        order = [inp["x"], inp["timesteps"], inp["context"], inp["y"], sig]
+        want = ex.denoise_step(*order).clone()
+        make = lambda backend, w: spmd.SpmdUNetEngine(ex, B, 256, 384, 77, weights=w, backend=backend)  # noqa: E731
+    else:
+        from comfyui_parallelanything_b200.exec.wan_exec import WanExecutor
+        from comfyui_parallelanything_b200.models import wan
+        p = wan.wan_tiny_params()
+        torch.manual_seed(2)
+        ex = WanExecutor(wan.WanModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        inp = wan.example_inputs(p, B, frames=8, height=128, width=192, device=dev, dtype=torch.bfloat16)
+        x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
+        order = [x, t, c, sig]
+        want = ex.denoise_step(*order).clone()
+        make = lambda backend, w: spmd.SpmdWanEngine(ex, B, x.shape[2], 128, 192, c.shape[1], weights=w,  # noqa: E731
+                                                     backend=backend)
+    res = {}
+    for backend, tma_peer in (("fused", "1"), ("fused", "0"), ("nccl", "0")):
+        os.environ["PA_TMA_PEER"] = tma_peer
+        eng = make(backend, [60, 40][:world] if world == 2 else None)
+        for it in range(3):
+            if rank == 0:
+                eng.stage_inputs(*order)
+            out = eng.step()
+        torch.cuda.synchronize()
+        eng.check_error()
+        if rank == 0:
+            d = (out.float() - want.float()).abs()
+            res[f"{backend}_tma{tma_peer}"] = dict(max_abs=d.max().item(),
+                                                  mean_rel=d.mean().item() / want.float().abs().mean().item(), sizes=eng.sizes)
+        eng.close()
+    if rank == 0:
+        ok = all(v["mean_rel"] < 5e-3 for v in res.values())
+        print("PA_SPMD " + json.dumps(dict(family=family, world=world, ok=ok, results=res)), flush=True)
     dist.destroy_process_group()
     return 0
 
