@@ -58,11 +58,11 @@ __device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, flo
   float n0, n1;
   unpack2(nf, n0, n1);
   const unsigned long long f = add2(x, pack2(-n0, -n1));
-  unsigned long long p = pack2(0.009618129f, 0.009618129f);
-  p = fma2(p, f, pack2(0.05550411f, 0.05550411f));
-  p = fma2(p, f, pack2(0.2402265f, 0.2402265f));
-  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
-  p = fma2(p, f, pack2(1.0f, 1.0f));
+  // degree-3 minimax of 2^f on [-0.5, 0.5]: max relative error 7.5e-5 (P is rounded to bf16, 2^-9, right after)
+  unsigned long long p = pack2(0.05517167f, 0.05517167f);
+  p = fma2(p, f, pack2(0.24261113f, 0.24261113f));
+  p = fma2(p, f, pack2(0.69326097f, 0.69326097f));
+  p = fma2(p, f, pack2(0.99992806f, 0.99992806f));
   float p0, p1, xr0, xr1;
   unpack2(p, p0, p1);
   unpack2(xr, xr0, xr1);
@@ -87,14 +87,19 @@ struct Cfg {
   static constexpr uint32_t OFF_K = 2 * TILE;               // 2 stages
   static constexpr uint32_t OFF_V = 4 * TILE;               // 2 stages
   static constexpr uint32_t OFF_BAR = 6 * TILE;
-  static constexpr uint32_t SMEM = OFF_BAR + 256 + 1024;
+  static constexpr uint32_t OFF_XCHG = OFF_BAR + 256;       // float[2 tiles][2 parities][2 halves][128 rows]
+  static constexpr uint32_t SMEM = OFF_XCHG + 4096 + 1024;
 };
 
 // DBG (timing experiments only, results are garbage for DBG != 0), bit mask: 1 = skip the softmax math, 2 = skip the
 // TMEM read of S, 4 = Q.K^T issues one MMA instead of D/16, 8 = P.V issues one MMA instead of 8, 16 = P.V reads its
 // A operand from shared memory (SS form) instead of tensor memory.
-template <int D, int DBG>
-__global__ void __launch_bounds__(384, 1)
+// NS: softmax warpgroups per query tile.  NS = 2 splits every S row between two threads (key columns 0..63 / 64..127,
+// row maxima exchanged through shared memory): two warps per scheduler work on the same tile, so one warp's MUFU.EX2
+// stalls are filled with the other's FMA-pipe work and the  S -> P  latency (the period-setting chain once the MMAs
+// issue back to back) roughly halves.  640 threads, setmaxnreg 56 / 104 (640 x 96 registers at launch).
+template <int D, int DBG, int NS>
+__global__ void __launch_bounds__(128 + 256 * NS, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
                   long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
@@ -133,7 +138,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_full[i], 4 * NS);
       ptx::mbar_init(&o_full[i], 1);
     }
     ptx::fence_barrier_init();
@@ -254,70 +259,80 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       __syncwarp();
     }
   } else {
-    ptx::setmaxnreg_inc<208>();
+    ptx::setmaxnreg_inc<(NS == 2 ? 104 : 208)>();
     // ===================== softmax warpgroups =====================
-    const int x = (warp - 4) >> 2;                      // query tile of this warpgroup
+    constexpr int CW = 128 / NS;                        // key columns of every S row owned by this thread
+    constexpr int OW = D / NS;                          // output columns owned by this thread
+    const int wg = (warp - 4) >> 2;
+    const int x = wg / NS;                              // query tile of this warpgroup
+    const int half = wg - x * NS;
     const int q4 = warp & 3;
     const int r = q4 * 32 + lane;
+    const bool tracer = (q4 == 0 && lane == 0 && half == 0);
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
-    const uint32_t s_addr = lane_addr + x * 128;
-    const uint32_t o_addr = lane_addr + 256 + x * 128;
+    const uint32_t s_addr = lane_addr + x * 128 + half * CW;
+    const uint32_t p_addr = lane_addr + x * 128 + half * (CW / 2);     // bf16x2-packed P columns of this thread
+    const uint32_t o_addr = lane_addr + 256 + x * 128 + half * OW;
+    float* xchg = reinterpret_cast<float*>(smem + C::OFF_XCHG) + x * 512;
     float m_used = -INFINITY, l = 0.f;
     const unsigned long long sl2 = pack2(scale_log2, scale_log2);
 
     for (int j = 0; j < n_kv; ++j) {
       ptx::mbar_wait(&s_full[x], j & 1);
-      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 0);
+      if (tracer) PA_TR(2 + x, j, 0);
       ptx::tc_fence_after();
-      uint32_t sv[128];
-      {
-        uint32_t(&c0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
-        uint32_t(&c1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        uint32_t(&c2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[64]);
-        uint32_t(&c3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[96]);
-        if (DBG & 2) {
+      uint32_t sv[CW];
+      if (DBG & 2) {
 #pragma unroll
-          for (int i = 0; i < 128; ++i) sv[i] = 0x3c000000u + i + j;
-        } else {
-          ptx::tmem_ld_32x32b_x32(s_addr, c0);
-          ptx::tmem_ld_32x32b_x32(s_addr + 32, c1);
-          ptx::tmem_ld_32x32b_x32(s_addr + 64, c2);
-          ptx::tmem_ld_32x32b_x32(s_addr + 96, c3);
-          ptx::tmem_ld_wait();
-        }
+        for (int i = 0; i < CW; ++i) sv[i] = 0x3c000000u + i + j;
+      } else {
+#pragma unroll
+        for (int c = 0; c < CW / 32; ++c)
+          ptx::tmem_ld_32x32b_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sv[c * 32]));
+        ptx::tmem_ld_wait();
       }
-      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 1);
+      if (tracer) PA_TR(2 + x, j, 1);
       if (DBG & 1) {
+        if (NS == 2) ptx::named_bar_sync(1 + x, 256);    // S of both halves is in registers before P overwrites it
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = (sv[c * 32 + 2 * i] >> 16) | (sv[c * 32 + 2 * i + 1] & 0xffff0000u);
-          ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);
+          ptx::tmem_st_32x32b_x16(p_addr + c * 16, pk);
         }
         ptx::tmem_st_wait();
         l = 1.f;
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&p_full[x]);
-        if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 4);
+        if (tracer) PA_TR(2 + x, j, 4);
         continue;
       }
-      const int kv_left = Lk - j * BN;
-      if (kv_left < BN) {
+      const int kv_left = Lk - j * BN - half * CW;
+      if (kv_left < CW) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < CW; ++i)
           if (i >= kv_left) sv[i] = 0xff800000u;
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 128; i += 8) {
+      for (int i = 0; i < CW; i += 8) {
         mx0 = fmax3(mx0, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
         mx1 = fmax3(mx1, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
         mx2 = fmax3(mx2, __uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5]));
         mx3 = fmax3(mx3, __uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7]));
       }
-      const float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(fmaxf(mx2, mx3), m_used));
+      float m_new = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (NS == 2) {
+        // the two column halves of every row exchange maxima; the barrier also orders "S in registers (both halves)"
+        // before the P stores below, which overwrite columns of S that belong to the other half
+        float* xb = xchg + (j & 1) * 256;
+        xb[half * 128 + r] = m_new;
+        ptx::named_bar_sync(1 + x, 256);
+        m_new = fmaxf(m_new, xb[(half ^ 1) * 128 + r]);
+      }
+      m_new = fmaxf(m_new, m_used);
       const bool need = (m_new - m_used) * scale_log2 > 8.0f;
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2f((m_used - m_new) * scale_log2) : 1.0f;
@@ -327,7 +342,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ptx::mbar_wait(&o_full[x], (j - 1) & 1);
           ptx::tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < OW / 32; ++c) {
             uint32_t t[32];
             ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
             ptx::tmem_ld_wait();
@@ -338,19 +353,21 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           ptx::tmem_st_wait();
         }
       }
-      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 2);
+      if (tracer) PA_TR(2 + x, j, 2);
       const float mneg_f = -m_used * scale_log2;
       const unsigned long long mneg = pack2(mneg_f, mneg_f);
       unsigned long long sum2 = pack2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CW / 32; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float a0, a1;
           const unsigned long long x2 =
               fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg);
-          if ((i >> 1) & 1) {
+          // 3 of every 8 pairs on the FMA pipe, 5 on the MUFU: per 128x128 tile that is 640 cycles of each pipe
+          // (MUFU.EX2: 16 lanes/clk/SM; a polynomial exp2 costs ~7 FMA-pipe lane-ops against 2 for scale + sum)
+          if ((0x52 >> ((i >> 1) & 7)) & 1) {
             exp2_poly2(x2, a0, a1);
           } else {
             unpack2(x2, a0, a1);
@@ -361,9 +378,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           __nv_bfloat162 hv = __floats2bfloat162_rn(a0, a1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hv);
         }
-        ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);    // P_X: keys 32c..32c+31 -> packed columns 16c..16c+15
+        ptx::tmem_st_32x32b_x16(p_addr + c * 16, pk);    // keys 32c..32c+31 of this half -> packed columns 16c..16c+15
       }
-      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 3);
+      if (tracer) PA_TR(2 + x, j, 3);
       ptx::tmem_st_wait();
       float s0, s1;
       unpack2(sum2, s0, s1);
@@ -371,17 +388,23 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[x]);
-      if (q4 == 0 && lane == 0) PA_TR(2 + x, j, 4);
+      if (tracer) PA_TR(2 + x, j, 4);
     }
 
+    if (NS == 2) {                                        // combine the two partial row sums
+      float* xl = xchg + (n_kv & 1) * 256;
+      xl[half * 128 + r] = l;
+      ptx::named_bar_sync(1 + x, 256);
+      l += xl[(half ^ 1) * 128 + r];
+    }
     ptx::mbar_wait(&o_full[x], (n_kv - 1) & 1);
     ptx::tc_fence_after();
     const int q_row = q0 + x * 128 + r;
     const float inv = 1.0f / l;
     const int b = bh / H, h = bh - b * H;
-    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D;
+    __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D + half * OW;
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OW / 32; ++c) {
       uint32_t t[32];
       ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
       ptx::tmem_ld_wait();
@@ -411,7 +434,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int D, int DBG>
+template <int D, int DBG, int NS = 2>
 static int launch(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                   int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs, float scale,
                   cudaStream_t st) {
@@ -430,13 +453,13 @@ static int launch(const void* q, const void* k, const void* v, void* out, long l
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<D, DBG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
   dim3 grid((Lq + 255) / 256, B * H);
-  attention2_kernel<D, DBG><<<grid, 384, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
+  attention2_kernel<D, DBG, NS><<<grid, 128 + 256 * NS, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
                                                    Lk, scale * 1.4426950408889634f);
   return (int)cudaGetLastError();
 }
@@ -452,14 +475,14 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
   return -11;
 }
 
-// timing experiments (D = 128 only): dbg 1..3, see attention2_kernel
+// timing experiments (D = 128 only): dbg = DBG mask (see attention2_kernel) + 128 for one softmax warpgroup per tile
 int attention2_debug(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                      int H, int Lq, int Lk, int dbg, const long long* qs, const long long* ks, const long long* vs,
                      float scale, cudaStream_t st) {
 #define PA_A2_DBG(N) \
-  if (dbg == N) return a2::launch<128, N>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
-  PA_A2_DBG(1) PA_A2_DBG(2) PA_A2_DBG(3) PA_A2_DBG(7) PA_A2_DBG(11) PA_A2_DBG(15) PA_A2_DBG(19) PA_A2_DBG(16)
-  PA_A2_DBG(64) PA_A2_DBG(67) PA_A2_DBG(79)
+  if (dbg == N) return a2::launch<128, N, 2>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st); \
+  if (dbg == N + 128) return a2::launch<128, N, 1>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
+  PA_A2_DBG(0) PA_A2_DBG(1) PA_A2_DBG(3) PA_A2_DBG(15) PA_A2_DBG(64) PA_A2_DBG(67)
 #undef PA_A2_DBG
   return -11;
 }

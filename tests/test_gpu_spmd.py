@@ -12,10 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-def test_spmd_fused_matches_single_gpu():
+@pytest.mark.parametrize("family", ["flux", "unet", "wan"])
+def test_spmd_fused_matches_single_gpu(family):
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
-           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "spmd_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "spmd_check.py"), family]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if l.startswith("PA_SPMD ")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
