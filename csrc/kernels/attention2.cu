@@ -78,6 +78,10 @@ __device__ long long g_trace[5 * 64 * 8];
       g_trace[((role) * 64 + (j)) * 8 + (slot)] = clock64();                          \
   } while (0)
 
+#ifndef PA_POLY_MASK
+#define PA_POLY_MASK 0x22
+#endif
+
 template <int D>
 struct Cfg {
   static constexpr int BN = 128;
@@ -115,9 +119,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* v_full = bars + 5;      // 2
   uint64_t* v_empty = bars + 7;     // 2
   uint64_t* s_full = bars + 9;      // 2 (tile A, B)
-  uint64_t* p_full = bars + 11;     // 2
+  uint64_t* p_full = bars + 11;     // 2: P_X keys 0..63 stored (the first four P.V MMAs may start)
   uint64_t* o_full = bars + 13;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_hi = bars + 15;       // 2: P_X keys 64..127 stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
@@ -138,7 +143,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       ptx::mbar_init(&v_full[i], 1);
       ptx::mbar_init(&v_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&p_full[i], 4 * NS);
+      ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&p_hi[i], 4);
       ptx::mbar_init(&o_full[i], 1);
     }
     ptx::fence_barrier_init();
@@ -227,7 +233,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           if (leader) {
             PA_TR(x, j, 0);
 #pragma unroll
-            for (int kk = 0; kk < ((DBG & 8) ? 1 : 8); ++kk) {
+            for (int kk = 0; kk < ((DBG & 8) ? 1 : 4); ++kk) {
               if (DBG & 16) {
                 const uint32_t off = ((kk >> 2) * SLICE + (kk & 3) * 32) >> 4;
                 ptx::mma_f16_ss(tmem_u + 256 + x * 128,
@@ -237,6 +243,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 ptx::mma_f16_ts(tmem_u + 256 + x * 128, tmem_u + x * 128 + kk * 8, vd + kk * 128, IDESC_PV,
                                 (j | kk) != 0);
               }
+            }
+          }
+          // second half of P_X (keys 64..127) is released separately: the first four MMAs overlap the rest of the exps
+          ptx::mbar_wait(&p_hi[x], j & 1);
+          ptx::tc_fence_after();
+          if (leader) {
+            if (!(DBG & 8)) {
+#pragma unroll
+              for (int kk = 4; kk < 8; ++kk)
+                ptx::mma_f16_ts(tmem_u + 256 + x * 128, tmem_u + x * 128 + kk * 8, vd + kk * 128, IDESC_PV, 1u);
             }
             ptx::tc_commit(&o_full[x]);
             if (x == 1) ptx::tc_commit(&v_empty[st]);
@@ -305,7 +321,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         l = 1.f;
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+        if (lane == 0) {
+          if (NS == 1 || half == 0) ptx::mbar_arrive(&p_full[x]);
+          if (NS == 1 || half == 1) ptx::mbar_arrive(&p_hi[x]);
+        }
         if (tracer) PA_TR(2 + x, j, 4);
         continue;
       }
@@ -365,9 +384,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           float a0, a1;
           const unsigned long long x2 =
               fma2(pack2(__uint_as_float(sv[c * 32 + i]), __uint_as_float(sv[c * 32 + i + 1])), sl2, mneg);
-          // 3 of every 8 pairs on the FMA pipe, 5 on the MUFU: per 128x128 tile that is 640 cycles of each pipe
-          // (MUFU.EX2: 16 lanes/clk/SM; a polynomial exp2 costs ~7 FMA-pipe lane-ops against 2 for scale + sum)
-          if ((0x52 >> ((i >> 1) & 7)) & 1) {
+          // PA_POLY_MASK: which of every 8 pairs take the FMA-pipe polynomial instead of MUFU.EX2 (16 lanes/clk/SM);
+          // tools/microbench/softmax_phase.cu: 2/8 is the fastest mix for one or two warps per scheduler
+          if ((PA_POLY_MASK >> ((i >> 1) & 7)) & 1) {
             exp2_poly2(x2, a0, a1);
           } else {
             unpack2(x2, a0, a1);
@@ -379,6 +398,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&hv);
         }
         ptx::tmem_st_32x32b_x16(p_addr + c * 16, pk);    // keys 32c..32c+31 of this half -> packed columns 16c..16c+15
+        if (NS == 1 && c == 1) {                         // keys 0..63 of P_X are complete: release the first four MMAs
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+        }
       }
       if (tracer) PA_TR(2 + x, j, 3);
       ptx::tmem_st_wait();
@@ -387,7 +412,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       l += s0 + s1;
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[x]);
+      if (lane == 0) ptx::mbar_arrive((NS == 1 || half == 1) ? &p_hi[x] : &p_full[x]);
       if (tracer) PA_TR(2 + x, j, 4);
     }
 
@@ -434,7 +459,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int D, int DBG, int NS = 2>
+template <int D, int DBG, int NS = 1>
 static int launch(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                   int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs, float scale,
                   cudaStream_t st) {

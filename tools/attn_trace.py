@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 from comfyui_parallelanything_b200 import ops  # noqa: E402
 
-masks = [int(a) for a in sys.argv[1:]] or [64, 192]
+masks = [int(a) for a in sys.argv[1:]] or [192]
 dev = torch.device("cuda:0")
 q, k, v = (torch.randn(2, 24, 4608, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
 out = torch.empty(2, 4608, 3072, dtype=torch.bfloat16, device=dev)

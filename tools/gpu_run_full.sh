@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU call: kernel checks, timeline, pytest -m gpu, headline bench (bf16 + fp8)
 mkdir -p gpurun_out
-timeout 200 python tools/attn_trace.py 64 > gpurun_out/attn_trace.log 2>&1
+timeout 200 python tools/attn_trace.py 192 > gpurun_out/attn_trace.log 2>&1
 timeout 300 python tools/gpu_check.py --only attention_speed > gpurun_out/attn_speed.log 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log
