@@ -26,6 +26,12 @@ def builder_for(module: nn.Module) -> Optional[Callable]:
                 and p.in_dim == 16:
             from .wan_exec import build_wan_executor
             return build_wan_executor
+    if fam == "zimage":
+        from ..models.zimage import ZImageModel
+        p = getattr(module, "params", None)
+        if isinstance(module, ZImageModel) and p.dim // p.n_heads == 128 and p.patch_size == 2 and p.in_channels == 16:
+            from .zimage_exec import build_zimage_executor
+            return build_zimage_executor
     if fam == "vae":
         from ..models.vae import VAEDecoder
         if isinstance(module, VAEDecoder):

@@ -225,6 +225,21 @@ class UNetExecutor(nn.Module):
     def parameters(self, recurse: bool = True):  # type: ignore[override]
         return iter(())
 
+    def invalidate_conditioning(self) -> None:
+        """Forget the cached cross-attention K/V (call when the prompt buffer is rewritten in place)."""
+        def walk(o):
+            if isinstance(o, _TBlock):
+                o._kv_sig = None
+            elif isinstance(o, (list, tuple)):
+                for v in o:
+                    walk(v)
+            elif hasattr(o, "__dict__") and not isinstance(o, torch.Tensor):
+                for v in vars(o).values():
+                    if isinstance(v, (list, tuple, _TBlock)) or (hasattr(v, "__dict__") and not isinstance(v, (torch.Tensor, nn.Module))):
+                        walk(v)
+        for seq in (self.inp, self.mid, self.outb):
+            walk(seq)
+
     def release(self) -> None:
         self.inp, self.mid, self.outb = [], [], []
 

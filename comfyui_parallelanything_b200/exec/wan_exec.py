@@ -89,6 +89,11 @@ class WanExecutor(nn.Module):
     def parameters(self, recurse: bool = True):  # type: ignore[override]
         return iter(())
 
+    def invalidate_conditioning(self) -> None:
+        """Forget the cached text embedding / cross-attention K/V (call when the prompt changes in place)."""
+        for ws in self._ws.values():
+            ws["ctx_sig"] = None
+
     def release(self) -> None:
         self.W.clear()
         self._ws.clear()

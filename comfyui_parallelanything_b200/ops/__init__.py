@@ -49,7 +49,7 @@ def native_ok(device) -> bool:
 
 
 EPI = {
-    "bias": 0, "gelu": 1, "silu": 2, "gate_res": 3, "qkv_rope": 4, "euler_unpatch": 5, "geglu": 6, "res": 7, "bias_bcast": 8,
+    "bias": 0, "gelu": 1, "silu": 2, "gate_res": 3, "qkv_rope": 4, "euler_unpatch": 5, "geglu": 6, "res": 7, "bias_bcast": 8, "swiglu": 9,
 }
 
 
@@ -96,6 +96,26 @@ def layernorm_modulate(x, out=None, scale=None, shift=None, gamma=None, beta=Non
         out = torch.empty_like(x)
     require().layernorm_modulate(x, out, scale, shift, gamma, beta, eps)
     return out
+
+
+def rmsnorm_modulate(x, out=None, weight=None, scale=None, gate=None, residual=None, eps: float = 1e-5,
+                     tanh_gate: bool = True):
+    """``out = [residual +] [tanh](gate) * rms(x) * weight * (1 + scale)`` per row (NextDiT / Z-Image blocks);
+    ``scale`` / ``gate``: per-sample [B, D] views.  ``out`` may alias ``residual``."""
+    if out is None:
+        out = torch.empty_like(x)
+    require().rmsnorm_mod(x, out, weight, scale, gate, residual, eps, tanh_gate)
+    return out
+
+
+def interleave_glu(wa: torch.Tensor, wg: torch.Tensor) -> torch.Tensor:
+    """Row-interleave value / gate projection weights (or biases) in groups of 32 for the ``geglu`` / ``swiglu``
+    GEMM epilogues: output column n/2 = a * act(g)."""
+    half = wa.shape[0]
+    if wa.dim() == 1:
+        return torch.stack([wa.view(half // 32, 32), wg.view(half // 32, 32)], 1).reshape(2 * half).contiguous()
+    k = wa.shape[1]
+    return torch.stack([wa.view(half // 32, 32, k), wg.view(half // 32, 32, k)], 1).reshape(2 * half, k).contiguous()
 
 
 def timestep_embedding(t: torch.Tensor, dim: int = 256, time_factor: float = 1000.0, max_period: float = 10000.0,

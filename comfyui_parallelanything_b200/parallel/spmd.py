@@ -269,6 +269,14 @@ class SpmdFluxEngine:
         self.comm_launches = self.ex.launches_per_step
         return self.buf["out"]
 
+    def new_conditioning(self) -> None:
+        """Collective by convention (every rank calls it): the conditioning staged next differs from the previous
+        one although it lives in the same heap buffer, so executors must drop what they cached from it (text
+        embeddings, cross-attention K/V, refined caption tokens)."""
+        inv = getattr(self.ex, "invalidate_conditioning", None)
+        if inv is not None:
+            inv()
+
     def check_error(self) -> None:
         v = int(self.err.item()) & 0xFFFFFFFF
         if v:
@@ -404,6 +412,32 @@ class SpmdWanEngine(SpmdFluxEngine):
     def _launch(self, loc: dict, fused: bool):
         if fused:
             x_bytes = self.C * self.T * self.H * self.W * 2
+            self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["sig"],
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                 x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2))
+            return None
+        return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["sig"])
+
+
+class SpmdZImageEngine(SpmdFluxEngine):
+    """Z-Image / NextDiT replicas (``exec/zimage_exec.py``): latent and timestep are pulled by the fused patch-embed
+    kernel from rank 0's heap, the caption features are read through a TMA descriptor on the peer mapping."""
+
+    tma_peer_inputs = ("ctx",)
+    kernel_pulled_inputs = ("x", "t")
+
+    def _latent_channels(self) -> int:
+        return self.ex.params.in_channels
+
+    def _make_spec(self, B: int) -> dict:
+        p, bf = self.ex.params, torch.bfloat16
+        shape = (B, self.C, self.H, self.W)
+        return {"x": (shape, bf), "t": ((B,), bf), "ctx": ((B, self.Lt, p.cap_feat_dim), bf),
+                "sig": ((B, 2), torch.float32), "out": (shape, bf)}
+
+    def _launch(self, loc: dict, fused: bool):
+        if fused:
+            x_bytes = self.C * self.H * self.W * 2
             self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], loc["sig"],
                                  out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
                                  x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2))

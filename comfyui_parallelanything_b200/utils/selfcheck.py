@@ -563,6 +563,68 @@ def wan_executor_tiny():
 
 
 @check
+def gemm_swiglu():
+    """w1 / w3 of a SwiGLU FFN as one GEMM over row-interleaved weights, ``a * silu(g)`` in the epilogue."""
+    M, K, H = 520, 256, 768
+    a, w3, w1 = _rand(M, K), _rand(H, K, scale=0.08, seed=1), _rand(H, K, scale=0.08, seed=2)
+    out = torch.empty(M, H, dtype=torch.bfloat16, device=_dev())
+    ops.gemm(a, ops.interleave_glu(w3, w1), "swiglu", out=out)
+    want = _gemm_ref(a, w3) * F.silu(_gemm_ref(a, w1))
+    return _cmp("gemm_swiglu", out, want, 0.012)
+
+
+@check
+def rmsnorm_modulate_kernel():
+    B, L, D = 2, 300, 3840
+    x, w = _rand(B, L, D), 1.0 + _rand(D, scale=0.1, seed=3)
+    sc, gt = _rand(B, 4 * D, scale=0.3, seed=4), _rand(B, 4 * D, seed=5)
+    res = _rand(B, L + 7, D, seed=6)[:, 7:]                       # strided residual / output view
+    xf = x.float()
+    rms = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+    got1 = ops.rmsnorm_modulate(x, weight=w, scale=sc[:, D:2 * D], eps=1e-5)
+    r1 = _cmp("rms_scale", got1, rms * (1 + sc[:, None, D:2 * D].float()), 0.01)
+    want2 = res.float() + torch.tanh(gt[:, None, 2 * D:3 * D].float()) * rms
+    ops.rmsnorm_modulate(x, out=res, weight=w, gate=gt[:, 2 * D:3 * D], residual=res, eps=1e-5)
+    r2 = _cmp("rms_gate_res", res, want2, 0.01)
+    got3 = ops.rmsnorm_modulate(_rand(3, 50, 2560, seed=8), weight=None, eps=1e-5)
+    x3 = _rand(3, 50, 2560, seed=8).float()
+    r3 = _cmp("rms_plain", got3, x3 * torch.rsqrt(x3.pow(2).mean(-1, keepdim=True) + 1e-5), 0.01)
+    r1["gate_res_mean_rel"], r1["plain_mean_rel"] = r2["mean_rel"], r3["mean_rel"]
+    r1["ok"] = r1["ok"] and r2["ok"] and r3["ok"]
+    r1["name"] = "rmsnorm_modulate_kernel"
+    return r1
+
+
+@check
+def zimage_executor_tiny():
+    from ..exec.zimage_exec import ZImageExecutor
+    from ..models import zimage
+    p = zimage.zimage_tiny_params()
+    torch.manual_seed(6)
+    m = zimage.ZImageModel(p).to(device=_dev(), dtype=torch.bfloat16).eval()
+    ex = ZImageExecutor(m, _dev())
+    oracle = zimage.ZImageModel(p).to(device=_dev(), dtype=torch.float32).eval()
+    oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    inp = zimage.example_inputs(p, 2, 256, 384, cap_len=40, device=_dev(), dtype=torch.bfloat16)
+    with torch.no_grad():
+        got = ex(**inp)
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+        eager = m(**inp)
+    r = _cmp("zimage_executor_tiny", got, want, 0.03)
+    r["eager_bf16_mean_rel"] = _cmp("eager", eager, want, 1.0)["mean_rel"]
+    r["launches"] = ex.launches_per_step
+    sig = torch.tensor([[1.0, 0.8], [0.6, 0.5]], device=_dev())
+    x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
+    nxt = ex.denoise_step(x, t, c, sig).clone()
+    want2 = inp["x"].float() + (sig[:, 1] - sig[:, 0])[:, None, None, None] * want
+    r2 = _cmp("zimage_euler", nxt, want2, 0.03)
+    r["euler_mean_rel"] = r2["mean_rel"]
+    r["second_step_launches"] = ex.launches_per_step            # caption path cached
+    r["ok"] = r["ok"] and r2["ok"]
+    return r
+
+
+@check
 def vae_decoder_executor():
     from ..exec.vae_exec import VAEDecoderExecutor
     from ..models import vae

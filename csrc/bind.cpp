@@ -203,6 +203,30 @@ static void layernorm_modulate(Tensor x, Tensor out, c10::optional<Tensor> scale
         "layernorm_modulate");
 }
 
+// out = [residual +] [tanh](gate) * rms(x) * weight * (1 + scale); scale / gate: [B, D] views (or [D]), any may be None
+static void rmsnorm_mod(Tensor x, Tensor out, c10::optional<Tensor> weight, c10::optional<Tensor> scale,
+                        c10::optional<Tensor> gate, c10::optional<Tensor> residual, double eps, bool tanh_gate) {
+  c10::cuda::CUDAGuard guard(x.device());
+  int b, rows, ob, orows;
+  long long ldx, xbs, ldo, obs, ldr = 0, rbs = 0;
+  view3(x, b, rows, ldx, xbs);
+  view3(out, ob, orows, ldo, obs);
+  TORCH_CHECK(b == ob && rows == orows, "rmsnorm_mod: shape mismatch");
+  long long mod_bs = 0;
+  const void *sc = nullptr, *gt = nullptr, *rs = nullptr;
+  if (scale) { sc = scale->data_ptr(); mod_bs = scale->dim() >= 2 ? scale->stride(0) : 0; TORCH_CHECK(scale->stride(-1) == 1); }
+  if (gate) { gt = gate->data_ptr(); long long s2 = gate->dim() >= 2 ? gate->stride(0) : 0; TORCH_CHECK(!scale || s2 == mod_bs, "scale/gate batch strides differ"); mod_bs = s2; TORCH_CHECK(gate->stride(-1) == 1); }
+  if (residual) {
+    int rb, rr;
+    view3(*residual, rb, rr, ldr, rbs);
+    TORCH_CHECK(rb == b && rr == rows, "rmsnorm_mod: residual shape mismatch");
+    rs = residual->data_ptr();
+  }
+  check(pa::rmsnorm_mod(x.data_ptr(), ldx, xbs, out.data_ptr(), ldo, obs, weight ? weight->data_ptr() : nullptr, sc, gt,
+                        mod_bs, rs, ldr, rbs, b, rows, (int)x.size(-1), (float)eps, tanh_gate ? 1 : 0, cur_stream()),
+        "rmsnorm_mod");
+}
+
 static void timestep_embedding(Tensor t, Tensor out, double time_factor, double max_period) {
   c10::cuda::CUDAGuard guard(t.device());
   TORCH_CHECK(out.dim() == 2 && out.stride(1) == 1 && out.scalar_type() == at::kBFloat16);
@@ -297,6 +321,20 @@ static void bcast_add(Tensor a, Tensor m, Tensor out) {
               out.is_contiguous());
   check(pa::bcast_add(a.data_ptr(), m.data_ptr(), out.data_ptr(), (int)a.size(0), (int)m.size(0), (int)a.size(1),
                       cur_stream()), "bcast_add");
+}
+
+// [B, R, D] -> [B, R, D] where each sample's [R, D] block is contiguous on both sides (e.g. the cached caption tokens
+// into the token buffer): one strided DMA copy (cudaMemcpy2DAsync), no kernel.
+static void copy_rows(Tensor src, Tensor dst) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.dim() == 3 && dst.dim() == 3 && src.sizes() == dst.sizes() && src.element_size() == dst.element_size());
+  TORCH_CHECK(src.stride(2) == 1 && dst.stride(2) == 1 && src.stride(1) == src.size(2) && dst.stride(1) == dst.size(2),
+              "copy_rows: per-sample blocks must be contiguous");
+  const size_t es = src.element_size();
+  const size_t width = (size_t)src.size(1) * src.size(2) * es;
+  cudaError_t e = cudaMemcpy2DAsync(dst.data_ptr(), (size_t)dst.stride(0) * es, src.data_ptr(), (size_t)src.stride(0) * es,
+                                    width, (size_t)src.size(0), cudaMemcpyDeviceToDevice, cur_stream());
+  check((int)e, "copy_rows");
 }
 
 static void softmax_rows(Tensor x, double scale) {
@@ -409,6 +447,10 @@ PYBIND11_MODULE(_C, m) {
   m.def("attention", &attention, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("scale"),
         py::arg("variant") = 1);
   m.def("attention2_trace", &attention2_trace);
+  m.def("copy_rows", &copy_rows);
+  m.def("rmsnorm_mod", &rmsnorm_mod, py::arg("x"), py::arg("out"), py::arg("weight") = py::none(),
+        py::arg("scale") = py::none(), py::arg("gate") = py::none(), py::arg("residual") = py::none(),
+        py::arg("eps") = 1e-5, py::arg("tanh_gate") = true);
   m.def("groupnorm_silu", &groupnorm_silu);
   m.def("cfg_euler_store", &cfg_euler_store);
   m.def("signal_flags", &signal_flags);

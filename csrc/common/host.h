@@ -27,6 +27,9 @@ int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, G
                cudaStream_t st);
 
 // out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
+int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,
+                const void* weight, const void* scale, const void* gate, long long mod_bs, const void* residual,
+                long long ldr, long long r_bs, int batch, int rows, int D, float eps, int tanh_gate, cudaStream_t st);
 int layernorm_modulate(const void* x, long long ldx, long long x_bstride, void* out, long long ldo,
                        long long o_bstride, const void* scale, const void* shift, long long mod_bstride,
                        const void* gamma, const void* beta, int batch, int rows, int D, float eps, cudaStream_t st);

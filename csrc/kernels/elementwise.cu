@@ -134,6 +134,106 @@ int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, 
   return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ RMSNorm + modulate / gated residual
+// NextDiT-style (Z-Image, Lumina) blocks:   out = rms(x) * w * (1 + scale)            (pre-norm + AdaLN scale)
+//                                           out = residual + tanh(gate) * rms(x) * w  (post-norm "sandwich" + gate)
+// One warp per row, row in registers; scale / gate are per-sample vectors (stride mod_bs), either may be null.
+template <int MAX_VEC>
+__global__ void __launch_bounds__(256) rms_mod_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long x_bs,
+                                                      __nv_bfloat16* __restrict__ out, long long ldo, long long o_bs,
+                                                      const __nv_bfloat16* __restrict__ weight,
+                                                      const __nv_bfloat16* __restrict__ scale,
+                                                      const __nv_bfloat16* __restrict__ gate, long long mod_bs,
+                                                      const __nv_bfloat16* residual, long long ldr, long long r_bs,
+                                                      int batch, int rows, int D, float eps, int tanh_gate) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * rows) return;
+  const int b = warp / rows, r = warp - b * rows;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + b * x_bs + static_cast<long long>(r) * ldx);
+  const int nvec = D >> 3;
+  uint4 buf[MAX_VEC];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      buf[i] = xr[idx];
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss += v[e] * v[e];
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / D + eps);
+  uint4* orow = reinterpret_cast<uint4*>(out + b * o_bs + static_cast<long long>(r) * ldo);
+  const uint4* rrow =
+      residual ? reinterpret_cast<const uint4*>(residual + b * r_bs + static_cast<long long>(r) * ldr) : nullptr;
+  const uint4* wv = weight ? reinterpret_cast<const uint4*>(weight) : nullptr;
+  const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + b * mod_bs) : nullptr;
+  const uint4* gt = gate ? reinterpret_cast<const uint4*>(gate + b * mod_bs) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= rstd;
+      if (wv) {
+        float g[8];
+        unpack8(__ldg(wv + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= g[e];
+      }
+      if (sc) {
+        float g[8];
+        unpack8(__ldg(sc + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= (1.0f + g[e]);
+      }
+      if (gt) {
+        float g[8];
+        unpack8(__ldg(gt + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= tanh_gate ? tanhf(g[e]) : g[e];
+      }
+      if (rrow) {
+        float g[8];
+        unpack8(rrow[idx], g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += g[e];
+      }
+      orow[idx] = pack8(v);
+    }
+  }
+}
+
+int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,
+                const void* weight, const void* scale, const void* gate, long long mod_bs, const void* residual,
+                long long ldr, long long r_bs, int batch, int rows, int D, float eps, int tanh_gate, cudaStream_t st) {
+  if (D % 8 || ldx % 8 || ldo % 8 || x_bs % 8 || o_bs % 8 || mod_bs % 8 || ldr % 8 || r_bs % 8) return -1;
+  const long long warps = static_cast<long long>(batch) * rows;
+  const int threads = 256;
+  const int blocks = static_cast<int>((warps * 32 + threads - 1) / threads);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto O = static_cast<__nv_bfloat16*>(out);
+  auto Wt = static_cast<const __nv_bfloat16*>(weight);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto G = static_cast<const __nv_bfloat16*>(gate);
+  auto R = static_cast<const __nv_bfloat16*>(residual);
+#define PA_RMS_MOD(V) \
+  rms_mod_kernel<V><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, Wt, SC, G, mod_bs, R, ldr, r_bs, batch, rows, D, \
+                                               eps, tanh_gate)
+  if (D <= 32 * 8 * 4) PA_RMS_MOD(4);
+  else if (D <= 32 * 8 * 12) PA_RMS_MOD(12);
+  else if (D <= 32 * 8 * 20) PA_RMS_MOD(20);
+  else return -2;
+#undef PA_RMS_MOD
+  return (int)cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ full-width RMSNorm (+ RoPE) in place
 // WAN-style q/k norm: RMS over the whole hidden dim (all heads), learned weight, then per-head RoPE on
 // adjacent pairs with a [L, 64] (cos, sin) table.  One warp per row, row held in registers.

@@ -100,7 +100,7 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
       bn = 64;
     } else {
       bn = pick_bn(p.N, m_tiles);
-      if (p.mode == EPI_GEGLU && bn == 160) bn = 128;   // the GEGLU epilogue walks 64-column [a|g] groups
+      if ((p.mode == EPI_GEGLU || p.mode == EPI_SWIGLU) && bn == 160) bn = 128;   // the GEGLU epilogue walks 64-column [a|g] groups
     }
   }
   if (p.mode == EPI_QKV_ROPE && bn < 128) return -12;

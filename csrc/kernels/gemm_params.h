@@ -15,6 +15,7 @@ enum EpiMode : int {
   EPI_GEGLU = 6,        // W rows interleaved [a(32) | g(32)]...: out[:, n/2] = a * gelu(g)
   EPI_RES = 7,          // out = residual + acc + bias
   EPI_BIAS_BCAST = 8,   // out = acc + bias + gate[b, n]   (per-sample channel bias, e.g. time embedding)
+  EPI_SWIGLU = 9,       // same interleaving as EPI_GEGLU: out[:, n/2] = a * silu(g)
 };
 
 struct GemmParams {

@@ -212,7 +212,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         }
       }
     }
-  } else if (p.mode == EPI_GEGLU) {
+  } else if (p.mode == EPI_GEGLU || p.mode == EPI_SWIGLU) {
     // columns come in groups of 64 = [a(32) | g(32)]; output column = n/2
     __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;
 #pragma unroll 1
@@ -229,7 +229,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         acc8(ra, g, p.bias ? p.bias + n + g * 8 : nullptr, a);
         acc8(rg, g, p.bias ? p.bias + n + 32 + g * 8 : nullptr, gt);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] = a[e] * gelu_erf(gt[e]);
+        for (int e = 0; e < 8; ++e) a[e] = a[e] * (p.mode == EPI_GEGLU ? gelu_erf(gt[e]) : gt[e] / (1.0f + __expf(-gt[e])));
         if (row_ok) st8(orow + n / 2 + g * 8, a);
       }
     }

@@ -235,3 +235,20 @@ def test_cfg_paired_split_keeps_pairs_together():
     assert chunks == [[0.0, 1.0, 4.0, 5.0], [2.0, 6.0], [3.0, 7.0]], chunks
     assert m._parallel_engine.metrics.counters["cfg_paired_steps"] == 1
     pa.cleanup_parallel_model(m)
+
+
+def test_zimage_layers_are_split_in_pipeline_mode_and_batch_split_matches():
+    """Z_IMAGE is one of the reference's tested families (README); its blocks live in ``layers`` (ADP:1156)."""
+    from comfyui_parallelanything_b200.models import zimage
+    torch.manual_seed(0)
+    p = zimage.zimage_tiny_params(dim=256, heads=2, layers=2)
+    m = zimage.ZImageModel(p).eval()
+    plain = copy.deepcopy(m)
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    assert isinstance(m.layers[0], pp.PipelineStage)
+    for batch in (1, 4):
+        inp = zimage.example_inputs(p, batch, 64, 64, cap_len=8, dtype=torch.float32)
+        with torch.no_grad():
+            assert torch.allclose(m(**inp), plain(**inp), atol=1e-5)
+    pa.cleanup_parallel_model(m)
+    assert not isinstance(m.layers[0], pp.PipelineStage)

@@ -99,3 +99,36 @@ def test_stranded_model_is_moved_back_to_its_load_device():
     m = nn.Sequential(nn.Linear(8, 8), nn.Linear(8, 8))
     nodes._repair_stranded(Patcher(), m)
     assert all(p.device == torch.device("cuda:0") for p in m.parameters())
+
+
+def _zimage_case(devs, batch):
+    from comfyui_parallelanything_b200.models import zimage
+    torch.manual_seed(2)
+    p = zimage.zimage_tiny_params()
+    m = zimage.ZImageModel(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    pa.ParallelAnything().setup_parallel(m, _chain(devs))
+    eng = m._parallel_engine
+    assert all(getattr(r, "pa_native", False) for r in eng.replicas.values()), "expected native Z-Image executors"
+    inp = zimage.example_inputs(p, batch, 256, 256, cap_len=32, device=devs[0], dtype=torch.bfloat16)
+    with torch.no_grad():
+        for _ in range(2):                  # second call: cached caption path
+            got = m(inp["x"], inp["timesteps"], context=inp["context"])
+        want = oracle(**{k: v.float() for k, v in inp.items()})
+    torch.cuda.synchronize()
+    rel = (got.float() - want).abs().mean().item() / want.abs().mean().item()
+    pa.cleanup_parallel_model(m)
+    return rel, eng
+
+
+def test_native_zimage_through_nodes():
+    rel, _ = _zimage_case(["cuda:0"], 3)
+    assert rel < 0.03, rel
+
+
+@pytest.mark.multigpu
+def test_multi_gpu_zimage_fused():
+    n = min(torch.cuda.device_count(), 4)
+    rel, eng = _zimage_case([f"cuda:{i}" for i in range(n)], 2 * n + 1)
+    assert rel < 0.03, rel
+    assert any(r.get("fused") for r in eng.metrics.rows), "fused in-process path was not taken"

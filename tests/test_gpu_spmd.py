@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 
-@pytest.mark.parametrize("family", ["flux", "unet", "wan"])
+@pytest.mark.parametrize("family", ["flux", "unet", "wan", "zimage"])
 def test_spmd_fused_matches_single_gpu(family):
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",

@@ -6,7 +6,7 @@ the timeout, the child is killed and a fresh one continues with the next check â
 cannot hide the state of the rest.
 
     python tools/gpu_check.py                 # all checks
-    python tools/gpu_check.py --only gemm     # substring filter
+    python tools/gpu_check.py --only gemm,attention     # substring filter(s)
 """
 from __future__ import annotations
 
@@ -52,7 +52,7 @@ def main() -> int:
     if a.child is not None:
         return child(a.child)
     from comfyui_parallelanything_b200.utils import selfcheck
-    todo = [n for n in selfcheck.CHECKS if a.only in n]
+    todo = [n for n in selfcheck.CHECKS if any(s in n for s in a.only.split(","))]
     results = {}
     while todo:
         p = subprocess.Popen([sys.executable, __file__, "--child"] + todo, stdout=subprocess.PIPE,

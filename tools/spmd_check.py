@@ -75,6 +75,17 @@ def other_family(family, rank, world, dev) -> int:
         order = [inp["x"], inp["timesteps"], inp["context"], inp["y"], sig]
         want = ex.denoise_step(*order).clone()
         make = lambda backend, w: spmd.SpmdUNetEngine(ex, B, 256, 384, 77, weights=w, backend=backend)  # noqa: E731
+    elif family == "zimage":
+        from comfyui_parallelanything_b200.exec.zimage_exec import ZImageExecutor
+        from comfyui_parallelanything_b200.models import zimage
+        p = zimage.zimage_tiny_params()
+        torch.manual_seed(4)
+        ex = ZImageExecutor(zimage.ZImageModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        inp = zimage.example_inputs(p, B, 256, 384, cap_len=40, device=dev, dtype=torch.bfloat16)
+        x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
+        order = [x, t, c, sig]
+        want = ex.denoise_step(*order).clone()
+        make = lambda backend, w: spmd.SpmdZImageEngine(ex, B, 256, 384, 40, weights=w, backend=backend)  # noqa: E731
     else:
         from comfyui_parallelanything_b200.exec.wan_exec import WanExecutor
         from comfyui_parallelanything_b200.models import wan
