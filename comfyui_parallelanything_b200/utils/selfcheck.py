@@ -563,6 +563,46 @@ def wan_executor_tiny():
 
 
 @check
+def gemm_2cta():
+    """CTA-pair (cta_group::2) GEMM kernel, selected with force_bn=512: numerics on even / ragged shapes and a
+    device-timed comparison with the one-CTA 128x256 kernel at a FLUX-like shape."""
+    res = {"name": "gemm_2cta", "ok": True}
+    for tag, (B, rows, K, N) in {"even": (2, 1024, 512, 768), "ragged": (3, 300, 320, 512), "one_tile": (1, 256, 64, 256)}.items():
+        a, w, b = _rand(B, rows, K, seed=1), _rand(N, K, scale=0.05, seed=2), _rand(N, seed=3)
+        out = torch.zeros(B, rows, N, dtype=torch.bfloat16, device=_dev())
+        ops.gemm(a, w, "bias", out=out, bias=b, force_bn=512)
+        r = _cmp(tag, out, _gemm_ref(a, w, b), 0.01)
+        res[tag + "_mean_rel"] = r["mean_rel"]
+        res["ok"] = res["ok"] and r["ok"]
+    # gated residual epilogue on a strided activation view
+    B, rows, K, N = 2, 640, 256, 512
+    big = _rand(B, rows + 64, K, seed=4)
+    a = big[:, 64:]
+    w, b, g = _rand(N, K, scale=0.05, seed=5), _rand(N, seed=6), _rand(B, N, seed=7)
+    resid = _rand(B, rows, N, seed=8)
+    want = resid.float() + g[:, None].float() * _gemm_ref(a, w, b)
+    out = resid.clone()
+    ops.gemm(a, w, "gate_res", out=out, bias=b, residual=out, gate=g, force_bn=512)
+    r = _cmp("gate_res", out, want, 0.012)
+    res["gate_res_mean_rel"] = r["mean_rel"]
+    res["ok"] = res["ok"] and r["ok"]
+    M, K, N = 18432, 3072, 9216
+    a, w, b = _rand(M, K, seed=9), _rand(N, K, scale=0.02, seed=10), _rand(N, seed=11)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=_dev())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for tag, bn in (("one_cta", 256), ("two_cta", 512), ("one_cta_again", 256), ("two_cta_again", 512)):
+        for _ in range(3):
+            ops.gemm(a, w, "bias", out=out, bias=b, force_bn=bn)
+        e0.record()
+        for _ in range(20):
+            ops.gemm(a, w, "bias", out=out, bias=b, force_bn=bn)
+        e1.record()
+        torch.cuda.synchronize()
+        res[tag + "_tflops"] = round(2.0 * M * N * K * 20 / e0.elapsed_time(e1) / 1e9, 1)
+    return res
+
+
+@check
 def gemm_swiglu():
     """w1 / w3 of a SwiGLU FFN as one GEMM over row-interleaved weights, ``a * silu(g)`` in the epilogue."""
     M, K, H = 520, 256, 768

@@ -7,6 +7,9 @@
 
 #include "../common/host.h"
 #include "gemm_tcgen05.cuh"
+#include "gemm_2cta.cuh"
+
+#include <cstdlib>
 
 namespace pa {
 
@@ -86,12 +89,60 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   return (int)cudaGetLastError();
 }
 
+// CTA-pair kernel (gemm_2cta.cuh): 256 x 256 tiles, one cluster of two CTAs per tile.
+static int launch_2cta(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, const GemmParams& p,
+                       cudaStream_t st) {
+  using Cfg = Gemm2CtaCfg;
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
+    uint64_t str[3] = {2, (uint64_t)lda * 2, (uint64_t)(p.batch > 1 ? a_bstride : (long long)p.rows * lda) * 2};
+    uint32_t box[3] = {64, 128, 1};
+    if (make_tmap(&ta, A, 3, dims, str, box, 2, nullptr)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    uint32_t box[2] = {64, 128};                       // each CTA of the pair loads half of the 256 B rows
+    if (make_tmap(&tb, W, 2, dims, str, box, 2, nullptr)) return -21;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  const int tiles = ((p.rows + 255) / 256) * p.batch * ((p.N + 255) / 256);
+  int grid = 2 * tiles < num_sms() ? 2 * tiles : (num_sms() & ~1);
+  gemm_bf16_2cta_kernel<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  return (int)cudaGetLastError();
+}
+
+// Large GEMMs whose N is a multiple of 256 use the CTA-pair kernel (1 437 vs 1 348 TFLOP/s at 18432 x 9216 x 3072,
+// profiles/selfcheck_gemm_2cta_run34.txt); PA_GEMM_2CTA=0 turns that off, force_bn == 512 / 256 selects a kernel
+// explicitly (numerics checks, A/B timing).
+static bool use_2cta_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("PA_GEMM_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // A: [batch, rows, K] with row stride lda and batch stride a_bstride (elements); W: [N, K] row stride ldw.
 int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, long long ldw, GemmParams p,
               int force_bn, cudaStream_t st) {
   if (p.K % 8 || lda % 8 || ldw % 8 || a_bstride % 8) return -10;   // TMA: 16-byte strides
   if (p.N % 32) return -11;
   const int m_tiles = ((p.rows + 127) / 128) * p.batch;
+  if (p.conv_taps == 0 &&
+      (force_bn == 512 || (force_bn == 0 && use_2cta_default() && p.N % 256 == 0 && p.rows >= 256 &&
+                           (long long)m_tiles * (p.N / 256) >= 2LL * num_sms())))
+    return launch_2cta(A, lda, a_bstride, W, ldw, p, st);
   int bn = force_bn;
   if (bn == 0) {
     if (p.mode == EPI_QKV_ROPE) {
