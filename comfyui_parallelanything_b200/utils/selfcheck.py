@@ -447,13 +447,31 @@ def attention_d64_strided():
 
 
 @check
+def attention_pair():
+    """CTA-pair attention kernel (variant 3): FLUX length, ragged key length, odd number of 256-row query blocks,
+    strided q/k/v views."""
+    res = {"name": "attention_pair", "ok": True}
+    for tag, (B, H, Lq, Lk) in {"flux": (1, 4, 4608, 4608), "ragged": (2, 3, 700, 333), "short": (1, 2, 100, 77)}.items():
+        qkv = _rand(B, max(Lq, Lk), 3, H, 128, seed=Lq)
+        q = qkv[:, :Lq, 0].permute(0, 2, 1, 3)
+        k = qkv[:, :Lk, 1].permute(0, 2, 1, 3)
+        v = qkv[:, :Lk, 2].permute(0, 2, 1, 3)
+        got = ops.attention(q, k, v, variant=3)
+        want = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(B, Lq, H * 128)
+        r = _cmp(tag, got, want, 0.02)
+        res[tag + "_mean_rel"] = r["mean_rel"]
+        res["ok"] = res["ok"] and r["ok"]
+    return res
+
+
+@check
 def attention_speed():
     """Device-timed FLUX-shaped attention (B=2, 24 heads, 4608 tokens) for both kernel variants."""
     q, k, v = (_rand(2, 24, 4608, 128, seed=i) for i in range(3))
     out = torch.empty(2, 4608, 3072, dtype=torch.bfloat16, device=_dev())
     res = {"name": "attention_speed", "ok": True}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for variant in (1, 2, 20, 151, 163):   # 20 + DBG mask (attention2.cu); +128: one softmax warpgroup per tile (default)
+    for variant in (1, 2, 3, 20, 151):   # 20 + DBG mask (attention2.cu); +128: one softmax warpgroup per tile (default)
         for _ in range(3):
             ops.attention(q, k, v, out=out, variant=variant)
         e0.record()

@@ -374,10 +374,16 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
           "attention2_debug");
     return;
   }
-  auto fn = variant == 2 ? pa::attention2_bf16 : pa::attention_bf16;
+  auto fn = (variant == 3 && D == 128) ? pa::attention3_bf16 : (variant >= 2 ? pa::attention2_bf16 : pa::attention_bf16);
   check(fn(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0), (int)q.size(0),
            (int)q.size(1), (int)q.size(2), (int)k.size(2), D, qs, ks, vs, (float)scale, cur_stream()),
         "attention");
+}
+
+static Tensor attention3_trace() {
+  Tensor t = at::zeros({7, 64, 8}, at::TensorOptions().dtype(at::kLong));
+  check(pa::attention3_trace_read(reinterpret_cast<long long*>(t.data_ptr<int64_t>())), "attention3_trace_read");
+  return t;
 }
 
 static Tensor attention2_trace() {
@@ -447,6 +453,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("attention", &attention, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("scale"),
         py::arg("variant") = 1);
   m.def("attention2_trace", &attention2_trace);
+  m.def("attention3_trace", &attention3_trace);
   m.def("copy_rows", &copy_rows);
   m.def("rmsnorm_mod", &rmsnorm_mod, py::arg("x"), py::arg("out"), py::arg("weight") = py::none(),
         py::arg("scale") = py::none(), py::arg("gate") = py::none(), py::arg("residual") = py::none(),

@@ -65,6 +65,11 @@ int attention_bf16(const void* q, const void* k, const void* v, void* out, long 
                    const long long* v_strides, float scale, cudaStream_t st);
 
 int attention2_trace_read(long long* host);
+int attention3_trace_read(long long* host);
+// CTA-pair ping-pong variant (csrc/kernels/attention3.cu, head dim 128 only); same contract
+int attention3_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                    int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
+                    const long long* v_strides, float scale, cudaStream_t st);
 // ping-pong variant (two query tiles per CTA, csrc/kernels/attention2.cu); same contract
 int attention2_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                     int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,

@@ -218,6 +218,28 @@ __device__ __forceinline__ void tma_load_3d_2cta(uint32_t smem_dst, const CUtens
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_2cta(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// A operand from tensor memory (each CTA's own 128 rows), B halves from both shared memories
+__device__ __forceinline__ void mma_f16_ts_2cta(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ void mma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                 uint32_t accumulate) {
   asm volatile(
@@ -238,13 +260,14 @@ __device__ __forceinline__ void tc_commit_2cta(uint64_t* bar, uint16_t cta_mask)
                : "memory");
 }
 
-// arrive on the barrier at this offset in CTA `cta` of the cluster
+// arrive on the barrier at this offset in CTA `cta` of the cluster (default .release.cta semantics: a
+// .release.cluster arrive costs ~1000 cycles per call - measured with the attention3 timeline)
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   asm volatile(
       "{\n\t"
       ".reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
       "}\n" ::"r"(smem_u32(bar)),
       "r"(cta)
       : "memory");
