@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-8}
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $N --steps 8 --warmup 4 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err
+tail -c 1500 gpurun_out/bench_n$N.json; tail -2 gpurun_out/bench_n$N.err
