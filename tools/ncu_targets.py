@@ -47,6 +47,22 @@ elif which == "gemm_sdxl":    # SDXL transformer to_out / proj: small K, residua
     e1.record()
     torch.cuda.synchronize()
     print("gemm_sdxl bias ms", e0.elapsed_time(e1) / 20, "TFLOP/s", 2.0 * M * N * K / (e0.elapsed_time(e1) / 20) / 1e9)
+elif which == "gemm_2cta":     # CTA-pair kernel at a FLUX single-block linear2-like shape
+    M, K, N = 9216, 3072, 9216
+    a, w, b = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.02, torch.randn(N, **bf)
+    out = torch.empty(M, N, **bf)
+    for _ in range(4):
+        ops.gemm(a, w, "bias", out=out, bias=b, force_bn=512)
+elif which == "attn3":
+    q, k, v = (torch.randn(1, 24, 4608, 128, **bf) for _ in range(3))
+    for _ in range(4):
+        ops.attention(q, k, v, variant=3)
+elif which == "rmsmod":
+    x, w_ = torch.randn(8, 4352, 3840, **bf), torch.randn(3840, **bf)
+    sc = torch.randn(8, 3840, **bf)
+    o = torch.empty_like(x)
+    for _ in range(4):
+        ops.rmsnorm_modulate(x, o, weight=w_, scale=sc)
 elif which == "attn2":
     q, k, v = (torch.randn(1, 24, 4608, 128, **bf) for _ in range(3))
     for _ in range(4):
