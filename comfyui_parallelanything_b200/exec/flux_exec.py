@@ -18,6 +18,7 @@ Per step: 19*13 + 38*4 + ~12 = ~410 kernel launches, optionally replayed as one 
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -25,11 +26,15 @@ import torch.nn as nn
 
 from .. import ops
 from ..models import flux as flux_model
+from ..utils import log
 from ..utils.log import nvtx_range
 
 
 def _bf16(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+_CAPTURE_LOCK = threading.Lock()
 
 
 class FluxExecutor(nn.Module):
@@ -121,6 +126,7 @@ class FluxExecutor(nn.Module):
             torch.cuda.empty_cache()
         self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
         self._ws: Dict[Tuple, dict] = {}
+        self._capture_stream = None
         self._graphs: Dict[Tuple, Tuple] = {}
         self.launches_per_step = 0
 
@@ -278,12 +284,30 @@ class FluxExecutor(nn.Module):
                 self._graphs = {k: v for k, v in self._graphs.items() if v != "seen"}
             self._graphs[key] = "seen"
         elif g == "seen":
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                body()
+            # Captures are serialised across executors: the in-process engine drives one executor per GPU from its
+            # own Python thread, and torch's capture prologue (synchronize / empty_cache) plus the default "global"
+            # capture mode make two concurrent captures - or a capture next to another thread's allocation - fail
+            # with cudaErrorIllegalState.  "thread_local" keeps other threads' CUDA calls legal while we record.
+            with _CAPTURE_LOCK:
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                if self._capture_stream is None:
+                    # torch's default capture stream is a per-process singleton living on whichever device captured
+                    # first: capturing another GPU's step on it records nothing (and the replay silently does nothing)
+                    self._capture_stream = torch.cuda.Stream(device=self.device)
+                try:
+                    with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
+                        body()
+                except Exception as e:                      # never lose a step to a failed capture
+                    log.warn("CUDA graph capture failed on %s (%s); staying eager for this shape", self.device, e)
+                    torch.cuda.synchronize(self.device)
+                    self._graphs[key] = "eager"
+                    body()
+                    return
             self._graphs[key] = graph
             graph.replay()
+        elif g == "eager":
+            body()
         else:
             g.replay()
 
