@@ -604,6 +604,22 @@ def gemm_2cta():
     r = _cmp("gate_res", out, want, 0.012)
     res["gate_res_mean_rel"] = r["mean_rel"]
     res["ok"] = res["ok"] and r["ok"]
+    # fused QKV (+ GELU'd MLP columns) epilogue: the pair kernel must reproduce the one-CTA kernel bit for bit
+    B, L, H, D = 2, 384, 2, 128
+    hid = H * D
+    x, w, b = _rand(B, L, hid, seed=12), _rand(3 * hid + 512, hid, scale=0.06, seed=13), _rand(3 * hid + 512, seed=14)
+    qs, ks = (1 + 0.1 * _rand(D).float()).bfloat16(), (1 + 0.1 * _rand(D, seed=3).float()).bfloat16()
+    _, table = _rope_table(L, _dev())
+    outs = []
+    for bn in (256, 512):
+        q = torch.zeros(B, H, L, D, dtype=torch.bfloat16, device=_dev())
+        k, v = torch.zeros_like(q), torch.zeros_like(q)
+        cat = torch.zeros(B, L, hid + 512, dtype=torch.bfloat16, device=_dev())
+        ops.gemm(x, w, "qkv_rope", q=q, k=k, v=v, q_scale=qs, k_scale=ks, rope=table, seq_off=0, out=cat, mlp_col_off=hid,
+                 bias=b, force_bn=bn)
+        outs.append(torch.cat([q.flatten(), k.flatten(), v.flatten(), cat[..., hid:].flatten()]))
+    res["qkv_rope_bit_identical"] = bool(torch.equal(outs[0], outs[1]))
+    res["ok"] = res["ok"] and res["qkv_rope_bit_identical"]
     M, K, N = 18432, 3072, 9216
     a, w, b = _rand(M, K, seed=9), _rand(N, K, scale=0.02, seed=10), _rand(N, seed=11)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=_dev())
@@ -614,6 +630,15 @@ def gemm_2cta():
         e0.record()
         for _ in range(20):
             ops.gemm(a, w, "bias", out=out, bias=b, force_bn=bn)
+        e1.record()
+        torch.cuda.synchronize()
+        res[tag + "_tflops"] = round(2.0 * M * N * K * 20 / e0.elapsed_time(e1) / 1e9, 1)
+    for tag, bn in (("gelu_one_cta", 256), ("gelu_two_cta", 512)):          # epilogue-heavy case
+        for _ in range(3):
+            ops.gemm(a, w, "gelu", out=out, bias=b, force_bn=bn)
+        e0.record()
+        for _ in range(20):
+            ops.gemm(a, w, "gelu", out=out, bias=b, force_bn=bn)
         e1.record()
         torch.cuda.synchronize()
         res[tag + "_tflops"] = round(2.0 * M * N * K * 20 / e0.elapsed_time(e1) / 1e9, 1)

@@ -8,8 +8,8 @@
 //   warp 0   TMA producer (both CTAs; transaction bytes of both land on the LEADER's `full` barrier)
 //   warp 1   MMA issuer (leader CTA only); commits multicast to `empty` / `tfull` of both CTAs
 //   warp 2   tensor-memory allocator (cta_group::2 form, same warp id in both CTAs)
-//   warps 4-7  epilogue (each CTA drains its own 128 x 256 accumulator half through the shared epilogue_tile<256>);
-//              `tempty` lives in the leader and counts the 8 epilogue warps of the pair (peer arrives remotely)
+//   warps 4-11 epilogue (each CTA drains its own 128 x 256 accumulator half, two warps per TMEM lane quadrant);
+//              `tempty` lives in the leader and counts the 16 epilogue warps of the pair (peer arrives remotely)
 #pragma once
 
 #include "gemm_tcgen05.cuh"
@@ -24,10 +24,10 @@ struct Gemm2CtaCfg {
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;                 // two 256-column accumulator stages
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 384;                        // 4 control warps + 8 epilogue warps
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const GemmParams p) {
   using Cfg = Gemm2CtaCfg;
@@ -59,7 +59,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 8);          // four epilogue warps of each CTA of the pair
+      ptx::mbar_init(&tempty[a], 16);         // eight epilogue warps of each CTA of the pair
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -146,7 +146,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===================== epilogue: this CTA's 128 rows of the pair's tile =====================
+    // Eight warps: two per TMEM lane quadrant, each draining 128 of the 256 accumulator columns.  The fused QKV
+    // epilogue (RMSNorm + RoPE per 128-wide head) and the erf-GELU epilogue cost ~15 instructions per element; with
+    // four warps they took about as long as the 48-K-block main loop of the next tile (85 % of peak vs 97 % for
+    // the plain epilogues), with eight they hide under it.
     const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r_in_tile = q4 * 32 + lane;
     int it = 0;
     for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
@@ -157,8 +162,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int acc = it & 1;
       ptx::mbar_wait(&tfull[acc], (it >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, taddr, b, row, row < p.rows, nt * BN);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN + half * (BN / 2);
+      if (nt * BN + half * (BN / 2) < p.N) epilogue_tile<BN / 2>(p, taddr, b, row, row < p.rows, nt * BN + half * (BN / 2));
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);        // the leader's MMA warp waits for all 8 warps
