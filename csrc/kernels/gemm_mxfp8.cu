@@ -55,7 +55,7 @@ __device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
 }
 
 template <int BN, int ACC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const uint8_t* __restrict__ sfa, const uint8_t* __restrict__ sfb, const GemmParams p) {
   using Cfg = Mx8Cfg<BN, ACC>;
@@ -81,7 +81,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);
+      ptx::mbar_init(&tempty[a], 8);          // eight epilogue warps
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -178,7 +178,12 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     __syncwarp();
   } else if (warp >= 4) {
+    // eight epilogue warps, two per TMEM lane quadrant: the fp8 main loop is twice as fast as the bf16 one, so the
+    // epilogue (same cost per element) would otherwise set the tile period (see gemm_2cta.cuh)
+    constexpr int H0 = BN >= 256 ? 128 : (BN > 128 ? 128 : 64);      // columns of the first half: 128 | 128 | 64
+    constexpr int H1 = BN - H0;                                      //                second half: 128 |  96 | 64
     const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int r_in_tile = q4 * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -190,7 +195,10 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_wait(&tfull[acc], ACC == 2 ? ((it >> 1) & 1) : (it & 1));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, taddr, b, row, row < p.rows, nt * BN);
+      if (half == 0)
+        epilogue_tile<H0>(p, taddr, b, row, row < p.rows, nt * BN);
+      else if (nt * BN + H0 < p.N)
+        epilogue_tile<H1>(p, taddr + H0, b, row, row < p.rows, nt * BN + H0);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -288,7 +296,7 @@ static int launch_mx8(const CUtensorMap& ta, const CUtensorMap& tb, const void* 
     attr_set[dev] = true;
   }
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_mxfp8_kernel<BN, ACC><<<grid, 256, Cfg::SMEM_BYTES, st>>>(ta, tb, static_cast<const uint8_t*>(sfa),
+  gemm_mxfp8_kernel<BN, ACC><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, static_cast<const uint8_t*>(sfa),
                                                                  static_cast<const uint8_t*>(sfb), p);
   return (int)cudaGetLastError();
 }

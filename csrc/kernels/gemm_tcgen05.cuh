@@ -50,7 +50,11 @@ struct GemmCfg {
   // two accumulator stages; the allocation must be a power of two >= 32 columns
   static constexpr uint32_t TMEM_COLS = 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512);
   static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 384;                // 4 control warps + 8 epilogue warps
+  // accumulator columns drained by the first / second warp of every TMEM lane quadrant (GLU epilogues walk
+  // 64-column groups, the QKV epilogue 128-column heads: both stay whole)
+  static constexpr int EPI_H0 = BN == 256 ? 128 : (BN == 160 ? 96 : 64);
+  static constexpr int EPI_H1 = BN - EPI_H0;       // 128 | 64 | 64 | 0
 };
 
 // 8 bf16 (16 B) <-> 8 floats
@@ -280,7 +284,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 }
 
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   using Cfg = GemmCfg<BN>;
@@ -310,7 +314,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);          // one arrive per epilogue warp
+      ptx::mbar_init(&tempty[a], 8);          // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async_smem();
@@ -411,8 +415,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps, thread == accumulator row) =====================
+    // ===================== epilogue (8 warps, thread == accumulator row x column half) =====================
     const int q4 = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;              // which part of the accumulator columns (see GemmCfg::EPI_H0/H1)
     const int r_in_tile = q4 * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -437,7 +442,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
 
-      epilogue_tile<BN>(p, taddr, b, row, row_ok, n0);
+      if (half == 0) {
+        epilogue_tile<Cfg::EPI_H0>(p, taddr, b, row, row_ok, n0);
+      } else if (Cfg::EPI_H1 > 0 && n0 + Cfg::EPI_H0 < p.N) {
+        epilogue_tile<(Cfg::EPI_H1 > 0 ? Cfg::EPI_H1 : 32)>(p, taddr + Cfg::EPI_H0, b, row, row_ok, n0 + Cfg::EPI_H0);
+      }
       // accumulator drained: hand it back to the MMA warp
       ptx::tc_fence_before();
       __syncwarp();
