@@ -110,6 +110,112 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const __nv_bfloat16* __rest
   }
 }
 
+// Specialised variants: which of gamma / beta / scale / shift exist is a compile-time flag set (bit 0 gamma, 1 beta,
+// 2 scale, 3 shift), so no predicated-off instructions are issued, and the affine part is folded into ONE fma per
+// element:  y = x * m + c  with  m = rstd * gamma * (1 + scale),  c = (-mean * rstd * gamma + beta) * (1 + scale) + shift.
+// The generic kernel above issued ~25 instructions per element (ncu: 43 % issue-slot utilisation, 2.2 TB/s); this is ~10.
+template <int MAX_VEC, int FLAGS>
+__global__ void __launch_bounds__(256) ln_mod_fast_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+                                                          long long x_bs, __nv_bfloat16* __restrict__ out, long long ldo,
+                                                          long long o_bs, const __nv_bfloat16* __restrict__ scale,
+                                                          const __nv_bfloat16* __restrict__ shift, long long mod_bs,
+                                                          const __nv_bfloat16* __restrict__ gamma,
+                                                          const __nv_bfloat16* __restrict__ beta, int batch, int rows,
+                                                          int D, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= batch * rows) return;
+  const int b = warp / rows, r = warp - b * rows;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + b * x_bs + static_cast<long long>(r) * ldx);
+  const int nvec = D >> 3;
+  uint4 buf[MAX_VEC];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) buf[i] = xr[idx];
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    if (lane + i * 32 < nvec) {
+      float v[8];
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s += v[e];
+        ss = fmaf(v[e], v[e], ss);
+      }
+    }
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  const float mean = s / D;
+  const float rstd = rsqrtf(fmaxf(ss / D - mean * mean, 0.f) + eps);
+  const float nmr = -mean * rstd;
+  uint4* orow = reinterpret_cast<uint4*>(out + b * o_bs + static_cast<long long>(r) * ldo);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + ((FLAGS & 4) ? b * mod_bs : 0));
+  const uint4* sh = reinterpret_cast<const uint4*>(shift + ((FLAGS & 8) ? b * mod_bs : 0));
+  const uint4* ga = reinterpret_cast<const uint4*>(gamma);
+  const uint4* be = reinterpret_cast<const uint4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAX_VEC; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nvec) {
+      float v[8], m[8], c[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { m[e] = rstd; c[e] = nmr; }
+      if (FLAGS & 1) {
+        float g[8];
+        unpack8(__ldg(ga + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { m[e] *= g[e]; c[e] *= g[e]; }
+      }
+      if (FLAGS & 2) {
+        float g[8];
+        unpack8(__ldg(be + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] += g[e];
+      }
+      if (FLAGS & 4) {
+        float g[8];
+        unpack8(__ldg(sc + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float t = 1.0f + g[e];
+          m[e] *= t;
+          c[e] *= t;
+        }
+      }
+      if (FLAGS & 8) {
+        float g[8];
+        unpack8(__ldg(sh + idx), g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) c[e] += g[e];
+      }
+      unpack8(buf[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], m[e], c[e]);
+      orow[idx] = pack8(v);
+    }
+  }
+}
+
+template <int FLAGS>
+static bool launch_ln_fast(int blocks, int threads, cudaStream_t st, const __nv_bfloat16* X, long long ldx, long long x_bs,
+                           __nv_bfloat16* O, long long ldo, long long o_bs, const __nv_bfloat16* SC,
+                           const __nv_bfloat16* SH, long long mod_bs, const __nv_bfloat16* G, const __nv_bfloat16* Bt,
+                           int batch, int rows, int D, float eps) {
+  if (D <= 32 * 8 * 4)
+    ln_mod_fast_kernel<4, FLAGS><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 12)
+    ln_mod_fast_kernel<12, FLAGS><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else if (D <= 32 * 8 * 20)
+    ln_mod_fast_kernel<20, FLAGS><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
+  else
+    return false;
+  return true;
+}
+
 int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,
                        const void* scale, const void* shift, long long mod_bs, const void* gamma, const void* beta,
                        int batch, int rows, int D, float eps, cudaStream_t st) {
@@ -123,6 +229,13 @@ int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, 
   auto SH = static_cast<const __nv_bfloat16*>(shift);
   auto G = static_cast<const __nv_bfloat16*>(gamma);
   auto Bt = static_cast<const __nv_bfloat16*>(beta);
+  const int flags = (G ? 1 : 0) | (Bt ? 2 : 0) | (SC ? 4 : 0) | (SH ? 8 : 0);
+#define PA_LN_FAST(F)                                                                                              \
+  if (flags == F && launch_ln_fast<F>(blocks, threads, st, X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, \
+                                      D, eps))                                                                    \
+    return (int)cudaGetLastError();
+  PA_LN_FAST(12) PA_LN_FAST(4) PA_LN_FAST(3) PA_LN_FAST(0)
+#undef PA_LN_FAST
   if (D <= 32 * 8 * 4)
     ln_mod_kernel<4><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, SC, SH, mod_bs, G, Bt, batch, rows, D, eps);
   else if (D <= 32 * 8 * 12)
