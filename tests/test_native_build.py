@@ -14,3 +14,33 @@ def test_extension_imports_on_cpu():
     assert not ops.native_ok("cpu")
     if not torch.cuda.is_available():
         assert not ops.native_ok("cuda:0")
+
+
+def test_glu_weight_interleaving_matches_epilogue_contract():
+    """geglu / swiglu GEMM epilogues read output column n/2 from rows [a(32) | g(32)] of each 64-row group."""
+    import torch
+    from comfyui_parallelanything_b200 import ops
+    wa = torch.arange(64 * 4, dtype=torch.float32).view(64, 4)
+    wg = -wa
+    w = ops.interleave_glu(wa, wg)
+    assert w.shape == (128, 4)
+    assert torch.equal(w[0:32], wa[0:32]) and torch.equal(w[32:64], wg[0:32])
+    assert torch.equal(w[64:96], wa[32:64]) and torch.equal(w[96:128], wg[32:64])
+    b = ops.interleave_glu(torch.arange(64.0), -torch.arange(64.0))
+    assert torch.equal(b[:32], torch.arange(32.0)) and torch.equal(b[32:64], -torch.arange(32.0))
+
+
+def test_zimage_family_is_registered_for_the_native_executor():
+    import torch
+    from comfyui_parallelanything_b200 import exec as pa_exec
+    from comfyui_parallelanything_b200.models import zimage
+    m = zimage.ZImageModel(zimage.zimage_tiny_params())
+    assert pa_exec.builder_for(m) is not None
+    ids = zimage.ZImageModel.make_ids(2, 3, 2, 2, "cpu")
+    assert ids.shape == (2, 7, 3)
+    assert ids[0, :3, 0].tolist() == [1.0, 2.0, 3.0] and ids[0, 3:, 0].unique().tolist() == [4.0]
+    assert ids[0, 3:, 1].tolist() == [0.0, 0.0, 1.0, 1.0] and ids[0, 3:, 2].tolist() == [0.0, 1.0, 0.0, 1.0]
+    # head dim 64: no native schedule -> the engine falls back to a torch replica
+    assert pa_exec.builder_for(zimage.ZImageModel(zimage.ZImageParams(dim=256, n_heads=4, n_layers=1, n_refiner_layers=1,
+                                                                      ffn_hidden=256, cap_feat_dim=64, adaln_dim=64,
+                                                                      axes_dims=[16, 24, 24]))) is None
