@@ -28,6 +28,12 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
   u.x = f2bf(v[0], v[1]); u.y = f2bf(v[2], v[3]); u.z = f2bf(v[4], v[5]); u.w = f2bf(v[6], v[7]);
   return u;
 }
+// MUFU.TANH (abs error ~2^-11): plenty for a bf16 gate vector
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -251,7 +257,7 @@ int layernorm_modulate(const void* x, long long ldx, long long x_bs, void* out, 
 // NextDiT-style (Z-Image, Lumina) blocks:   out = rms(x) * w * (1 + scale)            (pre-norm + AdaLN scale)
 //                                           out = residual + tanh(gate) * rms(x) * w  (post-norm "sandwich" + gate)
 // One warp per row, row in registers; scale / gate are per-sample vectors (stride mod_bs), either may be null.
-template <int MAX_VEC>
+template <int MAX_VEC, int FLAGS>     // FLAGS: bit 0 weight, 1 scale, 2 gate, 3 residual present; -1 = decide at run time
 __global__ void __launch_bounds__(256) rms_mod_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long x_bs,
                                                       __nv_bfloat16* __restrict__ out, long long ldo, long long o_bs,
                                                       const __nv_bfloat16* __restrict__ weight,
@@ -283,9 +289,13 @@ __global__ void __launch_bounds__(256) rms_mod_kernel(const __nv_bfloat16* __res
   uint4* orow = reinterpret_cast<uint4*>(out + b * o_bs + static_cast<long long>(r) * ldo);
   const uint4* rrow =
       residual ? reinterpret_cast<const uint4*>(residual + b * r_bs + static_cast<long long>(r) * ldr) : nullptr;
-  const uint4* wv = weight ? reinterpret_cast<const uint4*>(weight) : nullptr;
-  const uint4* sc = scale ? reinterpret_cast<const uint4*>(scale + b * mod_bs) : nullptr;
-  const uint4* gt = gate ? reinterpret_cast<const uint4*>(gate + b * mod_bs) : nullptr;
+  const bool has_w = FLAGS < 0 ? weight != nullptr : (FLAGS & 1) != 0;
+  const bool has_sc = FLAGS < 0 ? scale != nullptr : (FLAGS & 2) != 0;
+  const bool has_gt = FLAGS < 0 ? gate != nullptr : (FLAGS & 4) != 0;
+  const bool has_res = FLAGS < 0 ? residual != nullptr : (FLAGS & 8) != 0;
+  const uint4* wv = reinterpret_cast<const uint4*>(weight);
+  const uint4* sc = reinterpret_cast<const uint4*>(scale + (has_sc ? b * mod_bs : 0));
+  const uint4* gt = reinterpret_cast<const uint4*>(gate + (has_gt ? b * mod_bs : 0));
 #pragma unroll
   for (int i = 0; i < MAX_VEC; ++i) {
     const int idx = lane + i * 32;
@@ -294,25 +304,25 @@ __global__ void __launch_bounds__(256) rms_mod_kernel(const __nv_bfloat16* __res
       unpack8(buf[i], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] *= rstd;
-      if (wv) {
+      if (has_w) {
         float g[8];
         unpack8(__ldg(wv + idx), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= g[e];
       }
-      if (sc) {
+      if (has_sc) {
         float g[8];
         unpack8(__ldg(sc + idx), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] *= (1.0f + g[e]);
       }
-      if (gt) {
+      if (has_gt) {
         float g[8];
         unpack8(__ldg(gt + idx), g);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] *= tanh_gate ? tanhf(g[e]) : g[e];
+        for (int e = 0; e < 8; ++e) v[e] *= tanh_gate ? tanh_fast(g[e]) : g[e];
       }
-      if (rrow) {
+      if (has_res) {
         float g[8];
         unpack8(rrow[idx], g);
 #pragma unroll
@@ -336,13 +346,24 @@ int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long lo
   auto SC = static_cast<const __nv_bfloat16*>(scale);
   auto G = static_cast<const __nv_bfloat16*>(gate);
   auto R = static_cast<const __nv_bfloat16*>(residual);
-#define PA_RMS_MOD(V) \
-  rms_mod_kernel<V><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, Wt, SC, G, mod_bs, R, ldr, r_bs, batch, rows, D, \
-                                               eps, tanh_gate)
-  if (D <= 32 * 8 * 4) PA_RMS_MOD(4);
-  else if (D <= 32 * 8 * 12) PA_RMS_MOD(12);
-  else if (D <= 32 * 8 * 20) PA_RMS_MOD(20);
-  else return -2;
+  // the combinations the NextDiT blocks use are compiled without run-time null checks (no predicated-off instructions)
+  const int flags = (Wt ? 1 : 0) | (SC ? 2 : 0) | (G ? 4 : 0) | (R ? 8 : 0);
+#define PA_RMS_MOD(V, F)                                                                                                  \
+  rms_mod_kernel<V, F><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, ldo, o_bs, Wt, SC, G, mod_bs, R, ldr, r_bs, batch, rows, \
+                                                  D, eps, tanh_gate)
+#define PA_RMS_MOD_D(F)                     \
+  {                                         \
+    if (D <= 32 * 8 * 4) PA_RMS_MOD(4, F);  \
+    else if (D <= 32 * 8 * 12) PA_RMS_MOD(12, F); \
+    else if (D <= 32 * 8 * 20) PA_RMS_MOD(20, F); \
+    else return -2;                         \
+  }
+  if (flags == 3) PA_RMS_MOD_D(3)
+  else if (flags == 13) PA_RMS_MOD_D(13)
+  else if (flags == 9) PA_RMS_MOD_D(9)
+  else if (flags == 1) PA_RMS_MOD_D(1)
+  else PA_RMS_MOD_D(-1)
+#undef PA_RMS_MOD_D
 #undef PA_RMS_MOD
   return (int)cudaGetLastError();
 }
