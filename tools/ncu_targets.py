@@ -53,6 +53,12 @@ elif which == "gemm_2cta":     # CTA-pair kernel at a FLUX single-block linear2-
     out = torch.empty(M, N, **bf)
     for _ in range(4):
         ops.gemm(a, w, "bias", out=out, bias=b, force_bn=512)
+elif which == "gemm_2cta_gelu":   # epilogue-heavy case the eight epilogue warps were added for
+    M, K, N = 9216, 3072, 12288
+    a, w, b = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.02, torch.randn(N, **bf)
+    out = torch.empty(M, N, **bf)
+    for _ in range(4):
+        ops.gemm(a, w, "gelu", out=out, bias=b, force_bn=512)
 elif which == "attn3":
     q, k, v = (torch.randn(1, 24, 4608, 128, **bf) for _ in range(3))
     for _ in range(4):
