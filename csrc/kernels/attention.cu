@@ -21,6 +21,7 @@
 
 #include "../common/host.h"
 #include "../common/ptx.cuh"
+#include "softmax_math.cuh"
 
 namespace pa {
 
@@ -40,64 +41,7 @@ struct AttnCfg {
   static constexpr uint32_t TMEM_COLS = 512;                       // S0 @0, S1 @128, O @256 (D columns)
 };
 
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-
-// 2^x for two packed floats without the SFU: n = round(x) via the 1.5*2^23 magic constant, 2^f on
-// [-0.5, 0.5] by a degree-4 polynomial (rel. error ~4e-5, far below bf16 resolution), exponent patched in
-// with integer adds.  x must be <= ~100; very negative inputs are clamped (result underflows to ~2^-126).
-__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, float& r1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  const unsigned long long x = pack2(x0, x1);
-  const unsigned long long magic = pack2(12582912.0f, 12582912.0f);
-  const unsigned long long nmagic = pack2(-12582912.0f, -12582912.0f);
-  const unsigned long long xr = add2(x, magic);                    // low mantissa bits = round(x)
-  const unsigned long long nf = add2(xr, nmagic);                  // round(x) as float
-  float n0, n1, f0, f1;
-  unpack2(nf, n0, n1);
-  const unsigned long long f = add2(x, pack2(-n0, -n1));
-  unsigned long long p = pack2(0.009618129f, 0.009618129f);
-  p = fma2(p, f, pack2(0.05550411f, 0.05550411f));
-  p = fma2(p, f, pack2(0.2402265f, 0.2402265f));
-  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
-  p = fma2(p, f, pack2(1.0f, 1.0f));
-  float p0, p1, xr0, xr1;
-  unpack2(p, p0, p1);
-  unpack2(xr, xr0, xr1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xr0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xr1) << 23));
-  (void)f0; (void)f1;
-}
+using namespace smx;
 
 template <int D>
 __global__ void __launch_bounds__(384, 1)
@@ -318,7 +262,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             fma2(pack2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2, mneg);
         if ((i >> 1) & 1) {
           // MUFU.EX2 is only 16 lanes/clk/SM on sm_100 (as slow as the two MMAs of this tile): every
-          // second pair goes through a Cody-Waite + degree-4 polynomial on the FMA pipe instead.
+          // second pair goes through a Cody-Waite + degree-3 polynomial on the FMA pipe instead.
           exp2_poly2(x2, a0, a1);
         } else {
           unpack2(x2, a0, a1);

@@ -23,60 +23,12 @@
 
 #include "../common/host.h"
 #include "../common/ptx.cuh"
+#include "softmax_math.cuh"
 
 namespace pa {
 namespace a3 {
 
-__device__ __forceinline__ float ex2f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// 2^x for two packed floats on the FMA pipe: Cody-Waite + degree-3 minimax (max relative error 7.5e-5)
-__device__ __forceinline__ void exp2_poly2(unsigned long long x2, float& r0, float& r1) {
-  float x0, x1;
-  unpack2(x2, x0, x1);
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
-  const unsigned long long x = pack2(x0, x1);
-  const unsigned long long xr = add2(x, pack2(12582912.0f, 12582912.0f));
-  const unsigned long long nf = add2(xr, pack2(-12582912.0f, -12582912.0f));
-  float n0, n1;
-  unpack2(nf, n0, n1);
-  const unsigned long long f = add2(x, pack2(-n0, -n1));
-  unsigned long long p = pack2(0.05517167f, 0.05517167f);
-  p = fma2(p, f, pack2(0.24261113f, 0.24261113f));
-  p = fma2(p, f, pack2(0.69326097f, 0.69326097f));
-  p = fma2(p, f, pack2(0.99992806f, 0.99992806f));
-  float p0, p1, xr0, xr1;
-  unpack2(p, p0, p1);
-  unpack2(xr, xr0, xr1);
-  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xr0) << 23));
-  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xr1) << 23));
-}
+using namespace smx;
 
 // timeline capture (TRACE = true instantiation only): [role 0..6][kv tile 0..63][slot 0..7] clock64 stamps of the
 // cluster (blockIdx.x = 2, 3; blockIdx.y = 1).  roles: 0/1 MMA thread (tile A / B), 2/3 leader softmax A / B,
