@@ -44,3 +44,25 @@ def test_zimage_family_is_registered_for_the_native_executor():
     assert pa_exec.builder_for(zimage.ZImageModel(zimage.ZImageParams(dim=256, n_heads=4, n_layers=1, n_refiner_layers=1,
                                                                       ffn_hidden=256, cap_feat_dim=64, adaln_dim=64,
                                                                       axes_dims=[16, 24, 24]))) is None
+
+
+def test_sass_uses_blackwell_paths_and_has_no_issue_waterfalls():
+    """Compile-time regression guard (needs only cuobjdump): the built library must contain the sm_100a tensor-core /
+    TMA instructions the design rests on - including the CTA-pair forms - and none of the ELECT / R2UR.BROADCAST /
+    BRA.U.ANY waterfall loops ptxas wraps around tcgen05 / TMA issue inside a ``lane == 0`` branch (~90 cycles per MMA,
+    DESIGN.md §5 "issue path")."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+    so = os.path.join(os.path.dirname(ops.__file__), "_C.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(so) or not os.path.exists(cuobjdump):
+        pytest.skip("no built library / cuobjdump")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, timeout=600).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTCQMMA", "UTMALDG", "UTMALDG.3D.2CTA", "UTCBAR.2CTA.MULTICAST",
+                     "LDTM", "STTM", "UTCCP"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS"
+    assert "BRA.U.ANY" not in sass, "tcgen05 / TMA issue fell back to a per-instruction waterfall loop"
