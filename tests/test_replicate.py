@@ -101,3 +101,42 @@ def test_ingest_state_dict_with_prefix(tmp_path):
     res = pack_cache.ingest_state_dict(dst, str(path), prefix="model.diffusion_model.", strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     _same(src, dst)
+
+
+def test_packed_weight_checkpoint_roundtrip_and_mismatch(tmp_path):
+    """SURVEY §5 checkpoint / resume of the executors' packed weight tables (exec/pack_cache.py), on a stand-in
+    executor so it runs without a GPU."""
+    import pytest
+    import torch
+    from comfyui_parallelanything_b200.exec import pack_cache
+
+    class FakeExec:
+        fp8 = False
+
+        def __init__(self, seed):
+            g = torch.Generator().manual_seed(seed)
+            self.W = {"a.w": torch.randn(4, 8, generator=g).bfloat16(), "a.b": None,
+                      "q.bytes": torch.randint(0, 255, (16,), generator=g, dtype=torch.uint8), "tile": 224}
+
+    src, dst = FakeExec(1), FakeExec(2)
+    path = str(tmp_path / "packed.pa")
+    assert pack_cache.save_packed(src, path) > 0
+    meta = pack_cache.load_packed_into(dst, path)
+    assert meta["class"] == "FakeExec" and meta["keys"] == 4
+    assert torch.equal(dst.W["a.w"], src.W["a.w"]) and torch.equal(dst.W["q.bytes"], src.W["q.bytes"])
+    assert dst.W["a.b"] is None and dst.W["tile"] == 224
+
+    class OtherExec(FakeExec):
+        pass
+    with pytest.raises(ValueError):
+        pack_cache.load_packed_into(OtherExec(3), path)                  # wrong executor class
+    bad = FakeExec(4)
+    bad.W["extra"] = torch.zeros(1)
+    with pytest.raises(KeyError):
+        pack_cache.load_packed_into(bad, path)                           # key set mismatch
+    shp = FakeExec(5)
+    shp.W["a.w"] = torch.zeros(2, 2).bfloat16()
+    with pytest.raises(ValueError):
+        pack_cache.load_packed_into(shp, path)                           # shape mismatch
+    with pytest.raises(TypeError):
+        pack_cache.save_packed(object(), path)                           # no packed table
