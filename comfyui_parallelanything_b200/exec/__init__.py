@@ -11,6 +11,37 @@ from typing import Callable, Optional
 import torch.nn as nn
 
 
+WORKSPACE_LIMIT = 6     # distinct (batch, resolution, text length) activation workspaces kept per executor
+
+
+def cache_workspace(cache: dict, key, ws: dict, device=None, on_evict: Optional[Callable] = None) -> dict:
+    """Insert ``ws`` into an executor's workspace cache, evicting the least recently used entry beyond
+    ``WORKSPACE_LIMIT`` (a ComfyUI session that walks through many resolutions must not pin gigabytes of activation
+    buffers per shape).  ``on_evict`` lets the executor drop anything that still points into the evicted buffers
+    (captured CUDA graphs); the device is synchronised first so no in-flight kernel uses them."""
+    cache[key] = ws
+    while len(cache) > WORKSPACE_LIMIT:
+        old = next(iter(cache))
+        if old == key:
+            break
+        if device is not None:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.synchronize(device)
+        if on_evict is not None:
+            on_evict(old)
+        del cache[old]
+    return ws
+
+
+def touch_workspace(cache: dict, key):
+    """LRU hit: move ``key`` to the most-recent end and return its workspace (or None)."""
+    ws = cache.get(key)
+    if ws is not None and next(reversed(cache)) != key:
+        cache[key] = cache.pop(key)
+    return ws
+
+
 def builder_for(module: nn.Module) -> Optional[Callable]:
     fam = getattr(module, "pa_family", None)
     if fam == "flux":

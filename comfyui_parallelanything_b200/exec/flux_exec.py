@@ -25,6 +25,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import cache_workspace, touch_workspace
 from ..models import flux as flux_model
 from ..utils import log
 from ..utils.log import nvtx_range
@@ -145,7 +146,7 @@ class FluxExecutor(nn.Module):
     # ------------------------------------------------------------------ workspaces
     def workspace(self, B: int, H: int, Wd: int, Lt: int) -> dict:
         key = (B, H, Wd, Lt)
-        ws = self._ws.get(key)
+        ws = touch_workspace(self._ws, key)
         if ws is not None:
             return ws
         d, hid, mlp = self.device, self.hid, self.mlp
@@ -168,7 +169,7 @@ class FluxExecutor(nn.Module):
         ids = flux_model.Flux.make_ids(m, 1, H, Wd, Lt, d)
         pe = flux_model.EmbedND(128, self.params.theta, self.params.axes_dim)(ids)     # [1,1,L,64,2,2]
         ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
-        self._ws[key] = ws
+        cache_workspace(self._ws, key, ws, device=self.device, on_evict=lambda _k: self._graphs.clear())
         return ws
 
     # ------------------------------------------------------------------ schedule

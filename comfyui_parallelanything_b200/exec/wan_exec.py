@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import cache_workspace, touch_workspace
 from ..models import flux as flux_model
 from ..models import wan as wan_model
 
@@ -101,7 +102,7 @@ class WanExecutor(nn.Module):
 
     def workspace(self, B: int, T: int, H: int, Wd: int, Lc: int) -> dict:
         key = (B, T, H, Wd, Lc)
-        ws = self._ws.get(key)
+        ws = touch_workspace(self._ws, key)
         if ws is not None:
             return ws
         d, dim = self.device, self.dim
@@ -126,7 +127,7 @@ class WanExecutor(nn.Module):
         pe = flux_model.EmbedND(dd, 10000, [dd - 4 * (dd // 6), 2 * (dd // 6), 2 * (dd // 6)])(ids)
         ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
         ws["ctx_sig"] = None
-        self._ws[key] = ws
+        cache_workspace(self._ws, key, ws, device=self.device)
         return ws
 
     def _heads(self, t: torch.Tensor, which: int, n: int) -> torch.Tensor:

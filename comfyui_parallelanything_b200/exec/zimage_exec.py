@@ -22,6 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import cache_workspace, touch_workspace
 from ..models import flux as flux_model
 from ..models import zimage as zimage_model
 
@@ -105,7 +106,7 @@ class ZImageExecutor(nn.Module):
 
     def workspace(self, B: int, H: int, Wd: int, Lc: int) -> dict:
         key = (B, H, Wd, Lc)
-        ws = self._ws.get(key)
+        ws = touch_workspace(self._ws, key)
         if ws is not None:
             return ws
         d, dim, p = self.device, self.dim, self.params
@@ -127,7 +128,7 @@ class ZImageExecutor(nn.Module):
         ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
         ws["ROPE_I"] = ws["ROPE"][Lc:].contiguous()
         ws["ctx_sig"] = None
-        self._ws[key] = ws
+        cache_workspace(self._ws, key, ws, device=self.device)
         return ws
 
     # ------------------------------------------------------------------ schedule

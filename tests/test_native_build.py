@@ -66,3 +66,15 @@ def test_sass_uses_blackwell_paths_and_has_no_issue_waterfalls():
                      "LDTM", "STTM", "UTCCP"):
         assert mnemonic in sass, f"{mnemonic} missing from the SASS"
     assert "BRA.U.ANY" not in sass, "tcgen05 / TMA issue fell back to a per-instruction waterfall loop"
+
+
+def test_executor_workspace_cache_is_lru_bounded():
+    from comfyui_parallelanything_b200 import exec as pa_exec
+    cache, evicted = {}, []
+    for i in range(pa_exec.WORKSPACE_LIMIT + 3):
+        pa_exec.cache_workspace(cache, ("shape", i), {"i": i}, on_evict=evicted.append)
+    assert len(cache) == pa_exec.WORKSPACE_LIMIT and evicted == [("shape", 0), ("shape", 1), ("shape", 2)]
+    assert pa_exec.touch_workspace(cache, ("shape", 3))["i"] == 3            # a hit makes it the most recent entry
+    pa_exec.cache_workspace(cache, ("shape", 99), {"i": 99}, on_evict=evicted.append)
+    assert ("shape", 3) in cache and evicted[-1] == ("shape", 4)
+    assert pa_exec.touch_workspace(cache, ("missing",)) is None
