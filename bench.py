@@ -12,6 +12,9 @@ One "denoise step" = model forward on the whole batch + the sampler's Euler upda
 
 ``value``  : device-timed steps/s (CUDA events, barrier + synchronize on both sides, max over ranks),
              inputs resident on the lead GPU.
+``--api``  : ``spmd`` (default; one process per GPU, ``parallel/spmd.py``) or ``nodes`` (ONE process drives all N
+             GPUs through the ComfyUI node API: ParallelDevice chain -> ParallelAnything.setup_parallel -> hooked
+             ``model.forward`` with a NEW input tensor every step, as a sampler does).
 ``e2e``    : same metric through the public API with, inside the timed region of every step, the
              host(pinned)->device copy of that step's inputs and a device->host read of the result.
 Both arms print one JSON line; the reference arm drives the UNMODIFIED reference
@@ -167,7 +170,66 @@ def quiet_stdout():
     sys.stdout = sys.stderr
 
 
-# ----------------------------------------------------------------------------- our arm
+# ----------------------------------------------------------------------------- shared
+def bench_config(batch: int, n: int) -> dict:
+    """Identical for both arms (the driver compares the dicts); free-text descriptions live in ``notes``."""
+    return {"model": MODEL_NAME, "global_batch": batch, "seq_len": 4608, "parallelism": f"dp{n}", "params_b": 11.9,
+            "l2": "no explicit flush: each step streams >= 12 GB of weights (>> 126 MB L2)"}
+
+
+def make_line(args, impl, ms, ms_e2e, clocks, h2d, d2h, launches, finite, dtype, notes, extra=None) -> dict:
+    value = 1000.0 / ms
+    line = {"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
+            "higher_is_better": True, "scaling": "strong",
+            # BASELINE.md's only published numbers are Z-Image Turbo on an RTX 3090 (+V100): a different model on
+            # different hardware, so there is no published number for this workload to divide by.
+            "vs_baseline": None,
+            "dtype": dtype, "data": "synthetic latents/conditioning of the named shape, random-init weights",
+            "impl": impl, "clocks": clocks,
+            "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "output_finite": finite, "config": bench_config(args.batch, args.gpus),
+            "notes": notes}
+    if extra:
+        line.update(extra)
+    return line
+
+
+def host_only_group(rank: int, world: int):
+    """Ranks that must stay off the GPUs (reference arm, ``--api nodes``): a gloo group, no CUDA context, no NCCL
+    communicator.  Rank != 0 sleeps in the final barrier and returns True (= caller should exit)."""
+    if world <= 1:
+        return False
+    import datetime
+    import torch.distributed as dist
+    dist.init_process_group("gloo", timeout=datetime.timedelta(hours=3))
+    if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
+        return True
+    return False
+
+
+def host_only_release(world: int):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def rel_err(a, b) -> dict:
+    a, b = a.float(), b.float()
+    d = (a - b).abs()
+    return {"max_abs": float(d.max()), "mean_rel": float(d.mean() / (b.abs().mean() + 1e-12)),
+            "max_rel_to_absmax": float(d.max() / (b.abs().max() + 1e-12))}
+
+
+DTYPE_NAMES = {"bf16": "bf16", "fp8": "fp8 (MXFP8 block-scaled tcgen05 GEMMs for the block linears = 99.9% of the FLOPs; "
+                                      "attention, norms, embedders bf16/fp32)"}
+
+
+# ----------------------------------------------------------------------------- our arm (one process per GPU)
 def run_ours(args) -> int:
     import torch
     rank, world, local = dist_env()
@@ -184,14 +246,31 @@ def run_ours(args) -> int:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     params, host = synthetic_inputs(B, pinned=True)
-    torch.manual_seed(1234)                          # identical random-init weights on every rank
-    with torch.device(dev):
-        model = flux.Flux(params, dtype=torch.bfloat16)
-    ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
-    del model
+    t_setup = time.perf_counter()
+    setup = {}
+    if world > 1 and args.replicate != "seed":
+        # weights exist on rank 0 only; every other rank receives the PACKED executor weights device-to-device
+        # (NVSwitch multicast kernel or NCCL broadcast) - the B200 answer to the reference's CPU-bounce clone loop
+        from comfyui_parallelanything_b200.parallel import replicate_nvl
+        torch.manual_seed(1234 if rank == 0 else 99)
+        with torch.device(dev):
+            model = flux.Flux(params, dtype=torch.bfloat16)
+        ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
+        del model
+        torch.cuda.synchronize()
+        setup = replicate_nvl.broadcast_executor(ex, src=0, method=args.replicate)
+    else:
+        torch.manual_seed(1234)                          # identical random-init weights on every rank
+        with torch.device(dev):
+            model = flux.Flux(params, dtype=torch.bfloat16)
+        ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
+        del model
     torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+    setup["setup_s"] = round(time.perf_counter() - t_setup, 2)
 
     result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+    extra = {"setup": setup}
     if world == 1:
         d = {k: v.to(dev) for k, v in host.items()}
         xs = ex._prep(d["x"], d["timesteps"], d["context"], d["y"], d["guidance"])
@@ -207,8 +286,8 @@ def run_ours(args) -> int:
             ex.denoise_step(stage["x"], stage["timesteps"], stage["context"], stage["y"], stage["guidance"],
                             stage["sig"], out=out_buf)
             result_host.copy_(out_buf, non_blocking=True)
-        comm = 0
-        parallelism = "dp1"
+        notes = {"parallelism": "one GPU, one CUDA graph per step",
+                 "step": "model forward + Euler update (fused into the last GEMM epilogue)"}
     else:
         from comfyui_parallelanything_b200.parallel.spmd import SpmdFluxEngine
         eng = SpmdFluxEngine(ex, B, 1024, 1024, 512, backend=args.backend)
@@ -226,8 +305,9 @@ def run_ours(args) -> int:
             out = eng.step()
             if rank == 0:
                 result_host.copy_(out, non_blocking=True)
-        parallelism = f"dp{world} ({args.backend}: in-kernel NVLink scatter/gather)" if args.backend == "fused" \
-            else f"dp{world} (nccl baseline)"
+        notes = {"parallelism": (f"one process per GPU ({args.backend}: in-kernel NVLink scatter/gather)"
+                                 if args.backend == "fused" else "one process per GPU (NCCL send/recv baseline)"),
+                 "step": "model forward + Euler update (fused into the last GEMM epilogue, peer stores to rank 0)"}
 
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = result_host.numel() * result_host.element_size()
@@ -235,11 +315,22 @@ def run_ours(args) -> int:
     if rank == 0:
         sampler.start()
     ms = timed(step_device, args.steps, args.warmup, world)
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), world)
     clocks = sampler.stop(args.gpus) if rank == 0 else {}
     if world > 1:
         eng.check_error()
-        launches = (ex.launches_per_step + 8) * args.steps
+        launches = eng.comm_launches * args.steps
+        # correctness of the multi-GPU result: one more SPMD step, then rank 0 recomputes the WHOLE batch on its own
+        # single-GPU executor from the same staged inputs and compares with the gathered output.
+        out = eng.step()
+        barrier_sync(world)
+        if rank == 0:
+            got = out.clone()
+            b = eng.buf
+            want = ex.denoise_step(b["x"], b["t"], b["ctx"], b["y"], b["g"], b["sig"]).clone()
+            torch.cuda.synchronize()
+            extra["output_matches_n1"] = rel_err(got, want)
+        barrier_sync(world)
     else:
         launches = ex.launches_per_step * args.steps
     finite = bool(torch.isfinite(result_host.float()).all().item()) if rank == 0 else True
@@ -248,19 +339,105 @@ def run_ours(args) -> int:
         import torch.distributed as dist
         dist.destroy_process_group()
     if rank == 0:
-        value = 1000.0 / ms
-        emit({"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
-              "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
-              "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / 0.0775, 2),
-              "dtype": "bf16" if args.dtype == "bf16" else "fp8 (MXFP8 block-scaled GEMMs; attention/norms bf16)",
-              "data": "synthetic latents/conditioning of the named shape, random-init weights",
-              "impl": "ours", "clocks": clocks,
-              "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-              "gpu_launches": launches, "output_finite": finite,
-              "config": {"model": MODEL_NAME, "global_batch": B, "seq_len": 4608, "parallelism": parallelism,
-                         "params_b": 11.9, "l2": "no explicit flush: each step streams 24 GB of weights (>> 126 MB L2)",
-                         "step": "model forward + Euler update (fused into the last GEMM epilogue)"}})
+        emit(make_line(args, "ours", ms, ms_e2e, clocks, h2d, d2h, launches, finite, DTYPE_NAMES[args.dtype], notes,
+                       extra))
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm, ONE process (node API)
+def run_nodes(args) -> int:
+    """What ComfyUI does: one process, the ParallelAnything node hooks ``model.forward``; a sampler calls it with a
+    NEW latent tensor every step and does the Euler update itself on the lead GPU."""
+    rank, world, local = dist_env()
+    if host_only_group(rank, world):
+        return 0
+    import torch
+    import comfyui_parallelanything_b200 as pa
+    from comfyui_parallelanything_b200.models import flux
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    lead = torch.device("cuda:0")
+    torch.cuda.set_device(lead)
+    B = args.batch
+    params, host = synthetic_inputs(B, pinned=True)
+    torch.manual_seed(1234)
+    t_setup = time.perf_counter()
+    with torch.device(lead):
+        model = flux.Flux(params, dtype=torch.bfloat16).eval()
+    chain = None
+    for i in range(args.gpus):
+        chain = pa.ParallelDevice().add_device(f"cuda:{i}", 100.0 / args.gpus, chain)[0]
+    if args.dtype == "fp8":
+        os.environ["PA_FP8"] = "1"
+    (model,) = pa.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
+    for i in range(args.gpus):
+        torch.cuda.synchronize(i)
+    setup_s = round(time.perf_counter() - t_setup, 2)
+    eng = model._parallel_engine
+    d = {k: v.to(lead) for k, v in host.items()}
+    stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
+    result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+
+    def euler(x, v, sig):
+        return x + (sig[:, 1] - sig[:, 0]).view(-1, 1, 1, 1).to(x.dtype) * v
+
+    state = {"x": d["x"]}
+
+    def step_device():
+        with torch.no_grad():
+            x = state["x"]
+            v = model(x, d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"])
+            state["x"] = euler(x, v, d["sig"])          # a NEW tensor every step, like a sampler loop
+
+    def step_e2e():
+        with torch.no_grad():
+            fresh = {k: torch.empty_like(v) for k, v in stage.items() if k in ("x", "timesteps")}
+            for k in stage:
+                (fresh.get(k, stage[k])).copy_(host[k], non_blocking=True)
+            x = fresh["x"]
+            v = model(x, fresh["timesteps"], context=stage["context"], y=stage["y"], guidance=stage["guidance"])
+            result_host.copy_(euler(x, v, stage["sig"]), non_blocking=True)
+
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = result_host.numel() * result_host.element_size()
+    sampler = ClockSampler()
+    sampler.start()
+
+    def sync_all():
+        for i in range(args.gpus):
+            torch.cuda.synchronize(i)
+
+    def timed_local(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        return e0.elapsed_time(e1) / steps
+
+    ms = timed_local(step_device, args.steps, max(args.warmup, 4))
+    ms_e2e = timed_local(step_e2e, args.steps, max(3, args.warmup // 2))
+    clocks = sampler.stop(args.gpus)
+    finite = bool(torch.isfinite(result_host.float()).all().item())
+    extra = {"api": "nodes", "setup": {"setup_s": setup_s}, "engine": eng.describe() if hasattr(eng, "describe") else {}}
+    if args.gpus > 1:
+        # multi-GPU result vs the lead replica alone on the same inputs
+        with torch.no_grad():
+            got = model(d["x"], d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"]).clone()
+            lead_rep = eng.slots[0].replica
+            want = lead_rep(d["x"], d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"]).clone()
+        sync_all()
+        extra["output_matches_n1"] = rel_err(got, want)
+    launches = sum(getattr(s.replica, "launches_per_step", 0) for s in eng.slots) * args.steps
+    pa.cleanup_parallel_model(model)
+    host_only_release(world)
+    notes = {"parallelism": "ONE process, ComfyUI node API: native sm_100a replicas, in-kernel NVLink scatter/gather, "
+                            "one CUDA graph per GPU replayed by native host threads",
+             "step": "hooked model.forward on a new latent tensor each step + torch Euler update on the lead GPU"}
+    emit(make_line(args, "ours", ms, ms_e2e, clocks, h2d, d2h, launches, finite, DTYPE_NAMES[args.dtype], notes, extra))
     return 0
 
 
@@ -274,101 +451,85 @@ def run_reference(args) -> int:
         if rank == 0:
             emit({"impl": "reference", "unavailable": str(e)[:300]})
         return 0
+    # The reference is ONE process that drives all N GPUs from its own threads (ADP:1361-1433).  The other torchrun
+    # ranks therefore stay off the GPUs entirely: no CUDA context, no NCCL communicator, no barrier kernel spinning
+    # on a device the reference's replicas run on.  They sleep in a host-only (gloo) barrier until rank 0 is done.
+    if host_only_group(rank, world):
+        return 0
     import torch
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ms = ms_e2e = None
-    clocks = {}
-    finite = True
+    from comfyui_parallelanything_b200.models import flux
     B = args.batch
-    h2d = d2h = 0
-    if rank == 0:
-        # The reference is single-process / multi-thread by construction: rank 0 drives all N GPUs
-        # through its own public API; the other torchrun ranks only take part in the barriers.
-        from comfyui_parallelanything_b200.models import flux
-        params, host = synthetic_inputs(B, pinned=True)
-        torch.manual_seed(1234)
-        lead = torch.device("cuda", 0)
-        # The reference rebuilds replicas with ``model_class(**config)`` (ADP:622) and copies weights INTO
-        # them (ADP:656), so a replica gets the process' default dtype: run this arm with bf16 as the
-        # default dtype (as a bf16 ComfyUI model would construct itself), otherwise clones would be fp32.
-        torch.set_default_dtype(torch.bfloat16)
-        with torch.device(lead):
-            model = flux.Flux(params, dtype=torch.bfloat16).eval()
-        # The reference rebuilds every replica on the host with ``model_class(**config)`` and then overwrites all
-        # of its weights (ADP:622, 640-656); random-initialising 11.9 B parameters on the CPU per replica only
-        # burns minutes of setup, so the (about to be overwritten) initialisation is skipped.  Timed steps are
-        # unaffected.
-        torch.nn.Linear.reset_parameters = lambda self: None
-        chain = None
-        pct = 100.0 / args.gpus
-        for i in range(args.gpus):
-            chain = ref.ParallelDevice().add_device(f"cuda:{i}", pct, chain)[0]
-        (model,) = ref.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
-        # The reference clones through ``source_model.cpu()`` in place (ADP:600-605) and leaves the original
-        # (= the replica it re-uses for the lead device) stranded on the host; in ComfyUI the model manager
-        # puts the MODEL back on ``load_device`` before sampling and the reference repairs it itself on the
-        # next setup (ADP:932-961).  The harness plays that role: only tensors that are on the CPU are moved
-        # (a blanket ``model.to(lead)`` would also drag the other replicas' blocks along, because the
-        # reference registers them as submodules of the lead model through ``ParallelBlock``).
+    params, host = synthetic_inputs(B, pinned=True)
+    torch.manual_seed(1234)
+    lead = torch.device("cuda", 0)
+    torch.cuda.set_device(lead)
+    # The reference rebuilds replicas with ``model_class(**config)`` (ADP:622) and copies weights INTO
+    # them (ADP:656), so a replica gets the process' default dtype: run this arm with bf16 as the
+    # default dtype (as a bf16 ComfyUI model would construct itself), otherwise clones would be fp32.
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(lead):
+        model = flux.Flux(params, dtype=torch.bfloat16).eval()
+    # The reference rebuilds every replica on the host with ``model_class(**config)`` and then overwrites all
+    # of its weights (ADP:622, 640-656); random-initialising 11.9 B parameters on the CPU per replica only
+    # burns minutes of setup, so the (about to be overwritten) initialisation is skipped.  Timed steps are
+    # unaffected.
+    torch.nn.Linear.reset_parameters = lambda self: None
+    chain = None
+    pct = 100.0 / args.gpus
+    t_setup = time.perf_counter()
+    for i in range(args.gpus):
+        chain = ref.ParallelDevice().add_device(f"cuda:{i}", pct, chain)[0]
+    (model,) = ref.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
+    # The reference clones through ``source_model.cpu()`` in place (ADP:600-605) and leaves the original
+    # (= the replica it re-uses for the lead device) stranded on the host; in ComfyUI the model manager
+    # puts the MODEL back on ``load_device`` before sampling and the reference repairs it itself on the
+    # next setup (ADP:932-961).  The harness plays that role: only tensors that are on the CPU are moved
+    # (a blanket ``model.to(lead)`` would also drag the other replicas' blocks along, because the
+    # reference registers them as submodules of the lead model through ``ParallelBlock``).
+    with torch.no_grad():
+        for t_ in list(model.parameters()) + list(model.buffers()):
+            if t_.device.type == "cpu":
+                t_.data = t_.data.to(lead)
+    for i in range(args.gpus):
+        torch.cuda.synchronize(i)
+    setup_s = round(time.perf_counter() - t_setup, 2)
+    d = {k: v.to(lead) for k, v in host.items()}
+    stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
+    result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+
+    def euler(x, v, sig):
+        return x + (sig[:, 1] - sig[:, 0]).view(-1, 1, 1, 1).to(x.dtype) * v
+
+    def step_device():
         with torch.no_grad():
-            for t_ in list(model.parameters()) + list(model.buffers()):
-                if t_.device.type == "cpu":
-                    t_.data = t_.data.to(lead)
-        d = {k: v.to(lead) for k, v in host.items()}
-        stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
-        result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
+            v = model(d["x"], d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"])
+            return euler(d["x"], v, d["sig"])
 
-        def euler(x, v, sig):
-            return x + (sig[:, 1] - sig[:, 0]).view(-1, 1, 1, 1).to(x.dtype) * v
-
-        def step_device():
-            with torch.no_grad():
-                v = model(d["x"], d["timesteps"], context=d["context"], y=d["y"], guidance=d["guidance"])
-                return euler(d["x"], v, d["sig"])
-
-        def step_e2e():
-            for k in stage:
-                stage[k].copy_(host[k], non_blocking=True)
-            with torch.no_grad():
-                v = model(stage["x"], stage["timesteps"], context=stage["context"], y=stage["y"],
-                          guidance=stage["guidance"])
-                result_host.copy_(euler(stage["x"], v, stage["sig"]), non_blocking=True)
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
-        d2h = result_host.numel() * result_host.element_size()
-    else:
-        def step_device():
-            return None
-        step_e2e = step_device
+    def step_e2e():
+        for k in stage:
+            stage[k].copy_(host[k], non_blocking=True)
+        with torch.no_grad():
+            v = model(stage["x"], stage["timesteps"], context=stage["context"], y=stage["y"],
+                      guidance=stage["guidance"])
+            result_host.copy_(euler(stage["x"], v, stage["sig"]), non_blocking=True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = result_host.numel() * result_host.element_size()
 
     sampler = ClockSampler()
-    if rank == 0:
-        sampler.start()
-    torch.cuda.set_device(0 if rank == 0 else local)
-    ms = timed(step_device, args.steps, args.warmup, world)
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
-    if rank == 0:
-        clocks = sampler.stop(args.gpus)
-        finite = bool(torch.isfinite(result_host.float()).all().item())
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
-    if rank == 0:
-        value = 1000.0 / ms
-        emit({"metric": METRIC, "value": round(value, 4), "unit": "steps/s", "n_gpus": args.gpus,
-              "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "sec_per_it": round(ms / 1e3, 4),
-              "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / 0.0775, 2),
-              "dtype": "bf16", "data": "synthetic latents/conditioning of the named shape, random-init weights",
-              "impl": "reference", "clocks": clocks,
-              "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
-                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-              "gpu_launches": 0, "output_finite": finite,
-              "config": {"model": MODEL_NAME, "global_batch": B, "seq_len": 4608,
-                         "parallelism": f"reference threads x{args.gpus} (single process, stock torch kernels)",
-                         "params_b": 11.9, "l2": "no explicit flush: each step streams 24 GB of weights (>> 126 MB L2)",
-                         "step": "model forward (reference hook) + torch Euler update on the lead GPU"}})
+    sampler.start()
+    # world=1 for the timing helpers: the whole reference lives in this process; its forward returns only after
+    # every replica's output has been copied to the lead GPU with blocking ``.to`` calls (ADP:1408), so CUDA
+    # events on the lead stream bracket all N GPUs' work.
+    ms = timed(step_device, args.steps, args.warmup, 1)
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), 1)
+    clocks = sampler.stop(args.gpus)
+    finite = bool(torch.isfinite(result_host.float()).all().item())
+    host_only_release(world)
+    notes = {"parallelism": f"reference threads x{args.gpus} (single process, stock torch kernels); idle torchrun ranks "
+                            "hold no CUDA context",
+             "step": "model forward (reference hook) + torch Euler update on the lead GPU"}
+    emit(make_line(args, "reference", ms, ms_e2e, clocks, h2d, d2h, 0, finite, "bf16", notes,
+                   {"setup": {"setup_s": setup_s}}))
     return 0
 
 
@@ -378,16 +539,23 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--api", default="spmd", choices=["spmd", "nodes"],
+                    help="spmd: one process per GPU (torchrun); nodes: ONE process drives all GPUs through the node API")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--backend", default=os.environ.get("PA_BACKEND", "fused"), choices=["fused", "nccl"])
+    ap.add_argument("--replicate", default="seed", choices=["seed", "nvls", "nccl"],
+                    help="N>1: how ranks != 0 get their weights: same RNG seed (default), NVSwitch multicast kernel, "
+                         "or NCCL broadcast of the packed executor weights from rank 0")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
-                    help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8); default bf16")
+    ap.add_argument("--dtype", default=os.environ.get("PA_BENCH_DTYPE", "bf16"), choices=["bf16", "fp8"],
+                    help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.api == "nodes":
+        return run_nodes(args)
     return run_ours(args)
 
 

@@ -329,18 +329,34 @@ class ParallelEngine:
                 # gather: write rows at their final offset on the lead device (no cat)
                 with self._lock:
                     if out_box["buf"] is None:
-                        out_box["buf"] = sp.output_like(out, batch, lead_dev)
+                        # Allocate from the LEAD stream's pool: every writer is ordered after ``lead_stream`` (peers
+                        # copy on it, the lead's own side stream waited on it), so a block the allocator hands back
+                        # cannot still be in use by work that is only ordered on some replica's side stream.
+                        if lead_stream is not None:
+                            with torch.cuda.stream(lead_stream):
+                                out_box["buf"] = sp.output_like(out, batch, lead_dev)
+                        else:
+                            out_box["buf"] = sp.output_like(out, batch, lead_dev)
                 buf = out_box["buf"]
                 if buf is None:                     # non-tensor outputs: fall back to concat
                     return sp.move_to_device(out, lead_dev)
+                if lead_stream is not None and dev == lead_dev and slot.stream is not None:
+                    _record_stream(buf, slot.stream)    # the lead replica writes its rows on its side stream
                 sp.write_rows(buf, out, offs[i])
                 return None
 
             if dev.type == "cuda":
                 with torch.cuda.device(dev):
-                    ctxs = [torch.cuda.stream(slot.stream)] if slot.stream is not None else []
+                    # ``torch.cuda.stream(s)`` also makes s.device current: enter the lead-stream context FIRST and
+                    # the replica's own stream LAST so the replica's forward runs with ITS device current (model
+                    # code that says ``device="cuda"`` / ``torch.cuda.current_stream()`` must land on ``dev``),
+                    # exactly as the reference guarantees with set_device + cuda.device(dev) (ADP:1370, 1386).
+                    ctxs = []
                     if lead_stream is not None and lead_dev != dev:
                         ctxs.append(torch.cuda.stream(lead_stream))
+                    if slot.stream is not None:
+                        ctxs.append(torch.cuda.stream(slot.stream))
+                    ctxs.append(torch.cuda.device(dev))
                     with _nested(ctxs):
                         if slot.stream is not None and lead_stream is not None and lead_dev == dev:
                             slot.stream.wait_stream(lead_stream)
@@ -496,6 +512,15 @@ class ParallelEngine:
                     log.warn("could not unload models: %s", e)
         if self.config.purge_cache:
             memory.aggressive_cleanup()
+
+
+def _record_stream(value, stream) -> None:
+    if isinstance(value, torch.Tensor):
+        if value.is_cuda:
+            value.record_stream(stream)
+    elif isinstance(value, (list, tuple)):
+        for v in value:
+            _record_stream(v, stream)
 
 
 class _nested:

@@ -43,33 +43,37 @@ def touch_workspace(cache: dict, key):
 
 
 def builder_for(module: nn.Module) -> Optional[Callable]:
-    fam = getattr(module, "pa_family", None)
+    """Pick the native executor for ``module`` by its STRUCTURE (attribute names + parameter shapes, as ComfyUI's
+    own model classes name them - ``exec/recognize.py``), never by ``isinstance`` of this repository's oracle classes:
+    the reference accepts any ``diffusion_model`` (/root/reference/any_device_parallel.py:917-930) and so do we."""
+    from . import recognize
+    got = recognize.identify(module)
+    if got is None:
+        return None
+    fam, p = got
     if fam == "flux":
-        from ..models.flux import Flux
-        if isinstance(module, Flux) and module.params.hidden_size // module.params.num_heads == 128 \
-                and module.params.patch_size == 2:
+        if p.hidden_size // p.num_heads == 128 and p.patch_size == 2 and p.hidden_size % 128 == 0:
             from .flux_exec import build_flux_executor
             return build_flux_executor
-    if fam == "wan":
-        from ..models.wan import WanModel
-        p = getattr(module, "params", None)
-        if isinstance(module, WanModel) and p.dim // p.num_heads == 128 and tuple(p.patch_size) == (1, 2, 2) \
-                and p.in_dim == 16:
+    elif fam == "wan":
+        if p.dim // p.num_heads == 128 and tuple(p.patch_size) == (1, 2, 2) and p.in_dim == 16:
             from .wan_exec import build_wan_executor
             return build_wan_executor
-    if fam == "zimage":
-        from ..models.zimage import ZImageModel
-        p = getattr(module, "params", None)
-        if isinstance(module, ZImageModel) and p.dim // p.n_heads == 128 and p.patch_size == 2 and p.in_channels == 16:
+    elif fam == "zimage":
+        if p.dim // p.n_heads == 128 and p.patch_size == 2 and p.in_channels == 16 and p.ffn_hidden % 32 == 0:
             from .zimage_exec import build_zimage_executor
             return build_zimage_executor
-    if fam == "vae":
-        from ..models.vae import VAEDecoder
-        if isinstance(module, VAEDecoder):
-            from .vae_exec import build_vae_executor
-            return build_vae_executor
-    if fam == "unet":
-        from . import unet_exec
-        if unet_exec.supports(module):
-            return unet_exec.build_unet_executor
+    elif fam == "vae":
+        from .vae_exec import build_vae_executor
+        return build_vae_executor
+    elif fam == "unet":
+        if p.supported:
+            from .unet_exec import build_unet_executor
+            return build_unet_executor
     return None
+
+
+def family_of(module: nn.Module) -> Optional[str]:
+    from . import recognize
+    got = recognize.identify(module)
+    return got[0] if got else None

@@ -18,14 +18,14 @@ Per step: 19*13 + 38*4 + ~12 = ~410 kernel launches, optionally replayed as one 
 """
 from __future__ import annotations
 
-import threading
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from .. import ops
-from . import cache_workspace, touch_workspace
+from . import cache_workspace, recognize, touch_workspace
+from .graphs import GraphCache
 from ..models import flux as flux_model
 from ..utils import log
 from ..utils.log import nvtx_range
@@ -33,9 +33,6 @@ from ..utils.log import nvtx_range
 
 def _bf16(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
-
-
-_CAPTURE_LOCK = threading.Lock()
 
 
 class FluxExecutor(nn.Module):
@@ -46,7 +43,9 @@ class FluxExecutor(nn.Module):
         super().__init__()
         ops.require()
         self.device = torch.device(device)
-        p = self.params = model.params
+        # hyper-parameters come from the module's STRUCTURE (weight shapes, ComfyUI attribute names), so a
+        # comfy.ldm.flux.model.Flux is packed exactly like the repository's own oracle class
+        p = self.params = recognize.params_of(model, "flux")
         self.hid, self.heads = p.hidden_size, p.num_heads
         if self.hid // self.heads != 128:
             raise ValueError("FluxExecutor is specialised for head_dim 128")
@@ -127,8 +126,7 @@ class FluxExecutor(nn.Module):
             torch.cuda.empty_cache()
         self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
         self._ws: Dict[Tuple, dict] = {}
-        self._capture_stream = None
-        self._graphs: Dict[Tuple, Tuple] = {}
+        self._graphs = GraphCache(self.device, enabled=cuda_graphs)
         self.launches_per_step = 0
 
     # nn.Module plumbing so engine utilities (module_device, .to("meta") on cleanup) work
@@ -270,48 +268,6 @@ class FluxExecutor(nn.Module):
         self.launches_per_step = n
         return out
 
-    def _maybe_graph(self, key, body) -> None:
-        """Replay the whole step (~410 launches) as ONE CUDA graph once the same buffers have been seen twice.
-        Every pointer the kernels use (inputs, peer mappings, output) is baked into the graph, so the graph is
-        keyed on all of them; any change falls back to eager launches.  Replays release the GIL, which is what
-        lets the in-process engine drive several GPUs from Python threads."""
-        if not self.cuda_graphs:
-            body()
-            return
-        g = self._graphs.get(key)
-        if g is None:
-            body()
-            if len(self._graphs) > 32:          # callers that pass fresh buffers every step never re-hit a key
-                self._graphs = {k: v for k, v in self._graphs.items() if v != "seen"}
-            self._graphs[key] = "seen"
-        elif g == "seen":
-            # Captures are serialised across executors: the in-process engine drives one executor per GPU from its
-            # own Python thread, and torch's capture prologue (synchronize / empty_cache) plus the default "global"
-            # capture mode make two concurrent captures - or a capture next to another thread's allocation - fail
-            # with cudaErrorIllegalState.  "thread_local" keeps other threads' CUDA calls legal while we record.
-            with _CAPTURE_LOCK:
-                torch.cuda.synchronize(self.device)
-                graph = torch.cuda.CUDAGraph()
-                if self._capture_stream is None:
-                    # torch's default capture stream is a per-process singleton living on whichever device captured
-                    # first: capturing another GPU's step on it records nothing (and the replay silently does nothing)
-                    self._capture_stream = torch.cuda.Stream(device=self.device)
-                try:
-                    with torch.cuda.graph(graph, stream=self._capture_stream, capture_error_mode="thread_local"):
-                        body()
-                except Exception as e:                      # never lose a step to a failed capture
-                    log.warn("CUDA graph capture failed on %s (%s); staying eager for this shape", self.device, e)
-                    torch.cuda.synchronize(self.device)
-                    self._graphs[key] = "eager"
-                    body()
-                    return
-            self._graphs[key] = graph
-            graph.replay()
-        elif g == "eager":
-            body()
-        else:
-            g.replay()
-
     # ------------------------------------------------------------------ public entry points
     def _prep(self, x, timesteps, context, y, guidance):
         d = self.device
@@ -339,21 +295,36 @@ class FluxExecutor(nn.Module):
             self._run(ws, x.data_ptr(), timesteps, context, y, guidance, out)
             return out
 
+    def _shard_args(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, y, guidance):
+        B = shape[0]
+        dummy = torch.empty(0, device=self.device)
+        _, timesteps, context, y, guidance = self._prep(dummy.new_empty((B, 1, 1, 1), dtype=torch.bfloat16),
+                                                         timesteps, context, y, guidance)
+        key = ("shard", tuple(shape), x_src_ptr, timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
+               y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, out_ptr, out_sample_off)
+        return key, timesteps, context, y, guidance
+
     @torch.no_grad()
     def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, y=None,
                       guidance=None, **_ignored):
         """In-process multi-GPU path: pull this replica's latent shard from the lead GPU's tensor (peer
-        pointer) inside the first kernel and store the velocity rows straight into the lead's output."""
+        pointer) inside the first kernel and store the velocity rows straight into the lead's output.
+        The engine stages every tensor argument into fixed device buffers, so the key (= all baked pointers) repeats
+        from step to step and the step replays as one CUDA graph."""
         with torch.cuda.device(self.device):
-            B = shape[0]
-            dummy = torch.empty(0, device=self.device)
-            _, timesteps, context, y, guidance = self._prep(dummy.new_empty((B, 1, 1, 1), dtype=torch.bfloat16),
-                                                             timesteps, context, y, guidance)
-            ws = self.workspace(B, shape[2], shape[3], context.shape[1])
-            key = ("shard", tuple(shape), x_src_ptr, timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
-                   y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, out_ptr, out_sample_off)
-            self._maybe_graph(key, lambda: self._run(ws, x_src_ptr, timesteps, context, y, guidance, None,
-                                                     out_ptr=out_ptr, out_sample_off=out_sample_off))
+            key, timesteps, context, y, guidance = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr,
+                                                                     out_sample_off, y, guidance)
+            ws = self.workspace(shape[0], shape[2], shape[3], context.shape[1])
+            self._graphs.run(key, lambda: self._run(ws, x_src_ptr, timesteps, context, y, guidance, None,
+                                                    out_ptr=out_ptr, out_sample_off=out_sample_off))
+
+    def shard_graph_handle(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, y=None,
+                           guidance=None, **_ignored) -> int:
+        """``cudaGraphExec_t`` of the captured step for exactly these buffers (0 = not captured yet): lets the engine
+        hand the replay to a native host thread instead of calling ``forward_shard`` from Python."""
+        with torch.cuda.device(self.device):
+            key = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off, y, guidance)[0]
+        return self._graphs.exec_handle(key)
 
     @torch.no_grad()
     def denoise_step(self, x, timesteps, context, y, guidance, sigmas, out=None, out_ptr=None, out_sample_off=0,
@@ -377,7 +348,7 @@ class FluxExecutor(nn.Module):
                    y.data_ptr(), guidance.data_ptr() if guidance is not None else 0, sigmas.data_ptr(),
                    out.data_ptr() if out is not None else 0, out_ptr or 0, out_sample_off, x_src_ptr or 0,
                    t_src_ptr or 0, g_src_ptr or 0)
-            self._maybe_graph(key, body)
+            self._graphs.run(key, body)
             return out
 
 

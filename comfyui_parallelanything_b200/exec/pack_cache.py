@@ -19,19 +19,55 @@ from typing import Any, Dict
 import torch
 
 
-def _collect(executor) -> Dict[str, Any]:
+def packed_table(executor) -> Dict[str, Any]:
+    """name -> packed tensor (or small int/None) of an executor.  DiT executors keep a flat ``W`` dict; the UNet / VAE
+    executors hold their packed weights in small per-layer objects (``_Conv`` / ``_Lin`` / ``_GN`` ...), which are walked
+    into dotted paths (``inp.3.0.1.conv1.w``) - deterministic for a given architecture, so a table saved from one
+    executor loads into another built from the same model definition."""
     w = getattr(executor, "W", None)
     if isinstance(w, dict):
         return w
-    raise TypeError(f"{type(executor).__name__} does not expose a packed weight table")
+    table: Dict[str, Any] = {}
+    seen = set()
+
+    def walk(o, path):
+        if isinstance(o, torch.Tensor):
+            if id(o) not in seen:
+                seen.add(id(o))
+                table[path] = o
+        elif isinstance(o, (list, tuple)):
+            for i, v in enumerate(o):
+                walk(v, f"{path}.{i}")
+        elif isinstance(o, dict):
+            for k in sorted(o, key=str):
+                walk(o[k], f"{path}.{k}")
+        elif hasattr(o, "__dict__") and not isinstance(o, (torch.nn.Module, type)):
+            for k in sorted(vars(o)):
+                if not k.startswith("_"):
+                    walk(getattr(o, k), f"{path}.{k}")
+    for name in sorted(vars(executor)):
+        if name.startswith("_") or name in ("device", "training"):
+            continue
+        v = getattr(executor, name)
+        if isinstance(v, (torch.Tensor, list, tuple, dict)) or (hasattr(v, "__dict__")
+                                                                and not isinstance(v, (torch.nn.Module, type))):
+            walk(v, name)
+    if not table:
+        raise TypeError(f"{type(executor).__name__} does not expose any packed weights")
+    return table
+
+
+_collect = packed_table
+
+FORMAT = 2
 
 
 def save_packed(executor, path: str) -> int:
     """Write every packed tensor (bf16 / fp8 bytes / scale chunks / ints) to ``path``; returns bytes written."""
-    table = _collect(executor)
+    table = packed_table(executor)
     blob = {k: (v.detach().cpu() if isinstance(v, torch.Tensor) else v) for k, v in table.items()}
     meta = {"class": type(executor).__name__, "fp8": bool(getattr(executor, "fp8", False)),
-            "keys": len(blob), "format": 1}
+            "keys": len(blob), "format": FORMAT}
     tmp = path + ".tmp"
     torch.save({"meta": meta, "weights": blob}, tmp)
     os.replace(tmp, path)                       # atomic: a crash never leaves a truncated checkpoint
@@ -39,13 +75,21 @@ def save_packed(executor, path: str) -> int:
 
 
 def load_packed_into(executor, path: str, strict: bool = True) -> Dict[str, Any]:
-    """Copy a saved packed table into ``executor`` (same architecture / fp8 mode).  Returns the meta dict."""
-    ck = torch.load(path, map_location="cpu", mmap=True, weights_only=False)
+    """Copy a saved packed table into ``executor`` (same architecture / fp8 mode).  Returns the meta dict.
+    The file is read with ``weights_only=True``: a ``.pa`` checkpoint holds tensors, ints, None and a small meta
+    dict only, so unpickling never executes code from the file."""
+    ck = torch.load(path, map_location="cpu", mmap=True, weights_only=True)
     meta, blob = ck["meta"], ck["weights"]
-    table = _collect(executor)
+    if meta.get("format") not in (1, FORMAT):
+        raise ValueError(f"unknown packed-checkpoint format {meta.get('format')!r}")
+    table = packed_table(executor)
+    flat = isinstance(getattr(executor, "W", None), dict)
     if strict:
         if meta.get("class") != type(executor).__name__:
             raise ValueError(f"checkpoint is for {meta.get('class')}, not {type(executor).__name__}")
+        if bool(meta.get("fp8", False)) != bool(getattr(executor, "fp8", False)):
+            raise ValueError(f"checkpoint fp8={meta.get('fp8')} but the executor was built with "
+                             f"fp8={bool(getattr(executor, 'fp8', False))}")
         missing = [k for k in table if k not in blob]
         extra = [k for k in blob if k not in table]
         if missing or extra:
@@ -58,7 +102,7 @@ def load_packed_into(executor, path: str, strict: bool = True) -> Dict[str, Any]
                     raise ValueError(f"{k}: shape/dtype mismatch {tuple(cur.shape)}/{cur.dtype} vs "
                                      f"{tuple(v.shape)}/{v.dtype}")
                 cur.copy_(v, non_blocking=True)
-            elif not strict or k in table:
+            elif flat and (not strict or k in table):
                 table[k] = v
     return meta
 

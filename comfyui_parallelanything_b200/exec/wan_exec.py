@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from . import cache_workspace, touch_workspace
+from . import cache_workspace, recognize, touch_workspace
+from .graphs import GraphCache
 from ..models import flux as flux_model
 from ..models import wan as wan_model
 
@@ -38,7 +39,7 @@ class WanExecutor(nn.Module):
         super().__init__()
         ops.require()
         d = self.device = torch.device(device)
-        p = self.params = model.params
+        p = self.params = recognize.params_of(model, "wan")      # from weight shapes / ComfyUI attribute names
         self.dim, self.heads = p.dim, p.num_heads
         if p.dim // p.num_heads != 128 or tuple(p.patch_size) != (1, 2, 2) or p.in_dim != 16:
             raise ValueError("WanExecutor is specialised for head_dim 128, patch (1,2,2), 16 latent channels")
@@ -60,12 +61,12 @@ class WanExecutor(nn.Module):
             sa, ca = blk.self_attn, blk.cross_attn
             W[f"b{i}.qkv.w"] = torch.cat([_bf(sa.q.weight, d), _bf(sa.k.weight, d), _bf(sa.v.weight, d)], 0).contiguous()
             W[f"b{i}.qkv.b"] = torch.cat([_bf(sa.q.bias, d), _bf(sa.k.bias, d), _bf(sa.v.bias, d)], 0).contiguous()
-            W[f"b{i}.nq"], W[f"b{i}.nk"] = _bf(sa.norm_q.weight, d), _bf(sa.norm_k.weight, d)
+            W[f"b{i}.nq"], W[f"b{i}.nk"] = _bf(recognize.norm_scale(sa.norm_q), d), _bf(recognize.norm_scale(sa.norm_k), d)
             lin(f"b{i}.o", sa.o)
             lin(f"b{i}.cq", ca.q)
             W[f"b{i}.ckv.w"] = torch.cat([_bf(ca.k.weight, d), _bf(ca.v.weight, d)], 0).contiguous()
             W[f"b{i}.ckv.b"] = torch.cat([_bf(ca.k.bias, d), _bf(ca.v.bias, d)], 0).contiguous()
-            W[f"b{i}.cnq"], W[f"b{i}.cnk"] = _bf(ca.norm_q.weight, d), _bf(ca.norm_k.weight, d)
+            W[f"b{i}.cnq"], W[f"b{i}.cnk"] = _bf(recognize.norm_scale(ca.norm_q), d), _bf(recognize.norm_scale(ca.norm_k), d)
             lin(f"b{i}.co", ca.o)
             W[f"b{i}.n3.g"], W[f"b{i}.n3.b"] = _bf(blk.norm3.weight, d), _bf(blk.norm3.bias, d)
             lin(f"b{i}.f0", blk.ffn[0])
@@ -84,7 +85,7 @@ class WanExecutor(nn.Module):
         self.n_blocks = len(model.blocks)
         self.eps = p.eps
         self._ws: Dict[Tuple, dict] = {}
-        self._kv_cache: Dict[Tuple, torch.Tensor] = {}
+        self._graphs = GraphCache(self.device, enabled=cuda_graphs)
         self.launches_per_step = 0
 
     def parameters(self, recurse: bool = True):  # type: ignore[override]
@@ -98,7 +99,7 @@ class WanExecutor(nn.Module):
     def release(self) -> None:
         self.W.clear()
         self._ws.clear()
-        self._kv_cache.clear()
+        self._graphs.clear()
 
     def workspace(self, B: int, T: int, H: int, Wd: int, Lc: int) -> dict:
         key = (B, T, H, Wd, Lc)
@@ -127,13 +128,31 @@ class WanExecutor(nn.Module):
         pe = flux_model.EmbedND(dd, 10000, [dd - 4 * (dd // 6), 2 * (dd // 6), 2 * (dd // 6)])(ids)
         ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
         ws["ctx_sig"] = None
-        cache_workspace(self._ws, key, ws, device=self.device)
+        cache_workspace(self._ws, key, ws, device=self.device, on_evict=lambda _k: self._graphs.clear())
         return ws
 
     def _heads(self, t: torch.Tensor, which: int, n: int) -> torch.Tensor:
         """[B, L, n*dim] -> the ``which``-th [B, H, L, 128] strided view (no copy)."""
         b, l, _ = t.shape
         return t.view(b, l, n, self.heads, 128)[:, :, which].permute(0, 2, 1, 3)
+
+    def _prepare_ctx(self, ws, ctx) -> int:
+        """Text embedding + every block's cross-attention K/V (+ k RMSNorm): functions of the conditioning only, so
+        they run EAGERLY and only when the conditioning changed (tensor identity / version, or after
+        ``invalidate_conditioning``) - never inside the per-step CUDA graph, which reads the results from the
+        workspace's fixed ``CKV`` buffers (the reference re-sends constant conditioning every step)."""
+        sig = (ctx.data_ptr(), tuple(ctx.shape), ctx._version)
+        if ws["ctx_sig"] == sig:
+            return 0
+        W, dim = self.W, self.dim
+        C = ops.require()
+        ops.gemm(ctx, W["text0.w"], "gelu", out=ws["CTX_H"], bias=W["text0.b"])
+        ops.gemm(ws["CTX_H"], W["text2.w"], "bias", out=ws["CTX"], bias=W["text2.b"])
+        for i in range(self.n_blocks):
+            ops.gemm(ws["CTX"], W[f"b{i}.ckv.w"], "bias", out=ws["CKV"][i], bias=W[f"b{i}.ckv.b"])
+            C.rms_rope(ws["CKV"][i][:, :, :dim], W[f"b{i}.cnk"], None, self.eps)
+        ws["ctx_sig"] = sig
+        return 2 + 2 * self.n_blocks
 
     def _run(self, ws, x_ptr, t, ctx, out, x_in=None, sigmas=None, out_ptr=None, out_sample_off=0, t_ptr=None,
              x_copy=None):
@@ -153,41 +172,18 @@ class WanExecutor(nn.Module):
         C.bcast_add(ws["E"], W["head_shift"], ws["HSHIFT"])        # head uses e (not the 6-way projection)
         C.bcast_add(ws["E"], W["head_scale"], ws["HSCALE"])
         n += 8
-        # text embedding + cross-attention K/V: only when the conditioning changed
-        sig = (ctx.data_ptr(), tuple(ctx.shape), ctx._version)
-        if ws["ctx_sig"] != sig:
-            ops.gemm(ctx, W["text0.w"], "gelu", out=ws["CTX_H"], bias=W["text0.b"])
-            ops.gemm(ws["CTX_H"], W["text2.w"], "bias", out=ws["CTX"], bias=W["text2.b"])
-            for i in range(self.n_blocks):
-                ops.gemm(ws["CTX"], W[f"b{i}.ckv.w"], "bias", out=ws["CKV"][i], bias=W[f"b{i}.ckv.b"])
-                C.rms_rope(ws["CKV"][i][:, :, :dim], W[f"b{i}.cnk"], None, self.eps)
-            ws["ctx_sig"] = sig
-            n += 2 + 2 * self.n_blocks
 
         def mod(i, j):
             return MOD[:, i, j * dim:(j + 1) * dim]
 
-        dbg = getattr(self, "_dbg", None)
-        if dbg is not None:
-            dbg.update(x0=X.clone(), e=ws["E"].clone(), e0=ws["E0"].clone(), ctx=ws["CTX"].clone())
         for i in range(self.n_blocks):
             # ---- self attention
             ops.layernorm_modulate(X, XM, scale=mod(i, 1), shift=mod(i, 0), eps=self.eps)
-            if dbg is not None and i == 0:
-                dbg["xm0"] = XM.clone()
             ops.gemm(XM, W[f"b{i}.qkv.w"], "bias", out=QKV, bias=W[f"b{i}.qkv.b"])
-            if dbg is not None and i == 0:
-                dbg["qkv_raw"] = QKV.clone()
             C.rms_rope(QKV[:, :, :dim], W[f"b{i}.nq"], ROPE, self.eps)
             C.rms_rope(QKV[:, :, dim:2 * dim], W[f"b{i}.nk"], ROPE, self.eps)
-            if dbg is not None and i == 0:
-                dbg["qkv_rope"] = QKV.clone()
             ops.attention(self._heads(QKV, 0, 3), self._heads(QKV, 1, 3), self._heads(QKV, 2, 3), out=ATT)
-            if dbg is not None and i == 0:
-                dbg["att"] = ATT.clone()
             ops.gemm(ATT, W[f"b{i}.o.w"], "gate_res", out=X, residual=X, gate=mod(i, 2), bias=W[f"b{i}.o.b"])
-            if dbg is not None and i == 0:
-                dbg["x_sa"] = X.clone()
             # ---- text cross attention
             ops.layernorm_modulate(X, XM, gamma=W[f"b{i}.n3.g"], beta=W[f"b{i}.n3.b"], eps=self.eps)
             ops.gemm(XM, W[f"b{i}.cq.w"], "bias", out=ws["CQ"], bias=W[f"b{i}.cq.b"])
@@ -195,14 +191,10 @@ class WanExecutor(nn.Module):
             ops.attention(self._heads(ws["CQ"], 0, 1), self._heads(ws["CKV"][i], 0, 2), self._heads(ws["CKV"][i], 1, 2),
                           out=ATT)
             ops.gemm(ATT, W[f"b{i}.co.w"], "res", out=X, residual=X, bias=W[f"b{i}.co.b"])
-            if dbg is not None and i == 0:
-                dbg["x_ca"] = X.clone()
             # ---- FFN
             ops.layernorm_modulate(X, XM, scale=mod(i, 4), shift=mod(i, 3), eps=self.eps)
             ops.gemm(XM, W[f"b{i}.f0.w"], "gelu", out=FF, bias=W[f"b{i}.f0.b"])
             ops.gemm(FF, W[f"b{i}.f2.w"], "gate_res", out=X, residual=X, gate=mod(i, 5), bias=W[f"b{i}.f2.b"])
-            if dbg is not None and i == 0:
-                dbg["x_b0"] = X.clone()
             n += 14
         # ---- head: AdaLN + Linear + unpatchify (+ Euler, + peer store)
         ops.layernorm_modulate(X, XM, scale=ws["HSCALE"][:, 0], shift=ws["HSHIFT"][:, 0], eps=self.eps)
@@ -230,17 +222,35 @@ class WanExecutor(nn.Module):
             B, _, T, H, Wd = x.shape
             ws = self.workspace(B, T, H, Wd, context.shape[1])
             out = torch.empty_like(x)
+            self._prepare_ctx(ws, context)
             self._run(ws, x.data_ptr(), timesteps, context, out)
             return out
+
+    def _shard_args(self, x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off):
+        d = self.device
+        timesteps = timesteps.to(device=d, dtype=torch.bfloat16).contiguous()
+        context = context.to(device=d, dtype=torch.bfloat16).contiguous()
+        key = ("shard", tuple(shape), x_src_ptr, timesteps.data_ptr(), context.data_ptr(), tuple(context.shape), out_ptr,
+               out_sample_off)
+        return key, timesteps, context
 
     @torch.no_grad()
     def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, **_ignored):
         with torch.cuda.device(self.device):
-            d = self.device
-            timesteps = timesteps.to(device=d, dtype=torch.bfloat16).contiguous()
-            context = context.to(device=d, dtype=torch.bfloat16).contiguous()
+            key, timesteps, context = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off)
             ws = self.workspace(shape[0], shape[2], shape[3], shape[4], context.shape[1])
-            self._run(ws, x_src_ptr, timesteps, context, None, out_ptr=out_ptr, out_sample_off=out_sample_off)
+            self._prepare_ctx(ws, context)
+            self._graphs.run(key, lambda: self._run(ws, x_src_ptr, timesteps, context, None, out_ptr=out_ptr,
+                                                    out_sample_off=out_sample_off))
+
+    def shard_graph_handle(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int,
+                           **_ignored) -> int:
+        with torch.cuda.device(self.device):
+            key, _t, context = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off)
+            ws = self.workspace(shape[0], shape[2], shape[3], shape[4], context.shape[1])
+            if ws["ctx_sig"] != (context.data_ptr(), tuple(context.shape), context._version):
+                return 0                    # conditioning changed: take the Python path once (eager K/V precompute)
+        return self._graphs.exec_handle(key)
 
     @torch.no_grad()
     def denoise_step(self, x, timesteps, context, sigmas, out=None, out_ptr=None, out_sample_off=0,
@@ -250,9 +260,17 @@ class WanExecutor(nn.Module):
             ws = self.workspace(B, T, H, Wd, context.shape[1])
             if out is None and out_ptr is None:
                 out = ws["OUT"]
-            self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, out, x_in=x,
-                      sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
-                      x_copy=x if x_src_ptr is not None else None)
+            self._prepare_ctx(ws, context)
+
+            def body():
+                self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, out, x_in=x,
+                          sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
+                          x_copy=x if x_src_ptr is not None else None)
+
+            key = (tuple(x.shape), x.data_ptr(), timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
+                   sigmas.data_ptr(), out.data_ptr() if out is not None else 0, out_ptr or 0, out_sample_off,
+                   x_src_ptr or 0, t_src_ptr or 0)
+            self._graphs.run(key, body)
             return out
 
 

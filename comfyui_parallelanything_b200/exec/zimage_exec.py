@@ -22,7 +22,8 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from . import cache_workspace, touch_workspace
+from . import cache_workspace, recognize, touch_workspace
+from .graphs import GraphCache
 from ..models import flux as flux_model
 from ..models import zimage as zimage_model
 
@@ -39,7 +40,7 @@ class ZImageExecutor(nn.Module):
         super().__init__()
         ops.require()
         d = self.device = torch.device(device)
-        p = self.params = model.params
+        p = self.params = recognize.params_of(model, "zimage")   # from weight shapes / ComfyUI attribute names
         self.dim, self.heads = p.dim, p.n_heads
         if p.dim // p.n_heads != 128 or p.patch_size != 2 or p.in_channels != 16:
             raise ValueError("ZImageExecutor is specialised for head_dim 128, 2x2 patches, 16 latent channels")
@@ -60,14 +61,14 @@ class ZImageExecutor(nn.Module):
         def block(name: str, blk):
             a, f = blk.attention, blk.feed_forward
             W[name + ".qkv"] = _bf(a.qkv.weight, d)
-            W[name + ".qs"], W[name + ".ks"] = _bf(a.q_norm.weight, d), _bf(a.k_norm.weight, d)
+            W[name + ".qs"], W[name + ".ks"] = _bf(recognize.norm_scale(a.q_norm), d), _bf(recognize.norm_scale(a.k_norm), d)
             W[name + ".out"] = _bf(a.out.weight, d)
             W[name + ".w13"] = ops.interleave_glu(_bf(f.w3.weight, d), _bf(f.w1.weight, d))     # out = w3x * silu(w1x)
             W[name + ".w2"] = _bf(f.w2.weight, d)
             for k_, m_ in (("n1", blk.attention_norm1), ("n2", blk.attention_norm2), ("f1", blk.ffn_norm1),
                            ("f2", blk.ffn_norm2)):
                 W[f"{name}.{k_}"] = _bf(m_.weight, d)
-            if blk.modulation:
+            if getattr(blk, "modulation", hasattr(blk, "adaLN_modulation")):
                 self.mod_off[name] = sum(w.shape[0] for w in mod_w)
                 mod_w.append(_bf(blk.adaLN_modulation[1].weight, d))
                 mod_b.append(_bf(blk.adaLN_modulation[1].bias, d))
@@ -90,6 +91,7 @@ class ZImageExecutor(nn.Module):
         self.n_cr, self.n_nr, self.n_layers = len(model.context_refiner), len(model.noise_refiner), len(model.layers)
         self.eps = p.norm_eps
         self._ws: Dict[Tuple, dict] = {}
+        self._graphs = GraphCache(self.device, enabled=cuda_graphs)
         self.launches_per_step = 0
 
     def parameters(self, recurse: bool = True):  # type: ignore[override]
@@ -103,6 +105,7 @@ class ZImageExecutor(nn.Module):
     def release(self) -> None:
         self.W.clear()
         self._ws.clear()
+        self._graphs.clear()
 
     def workspace(self, B: int, H: int, Wd: int, Lc: int) -> dict:
         key = (B, H, Wd, Lc)
@@ -128,7 +131,7 @@ class ZImageExecutor(nn.Module):
         ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
         ws["ROPE_I"] = ws["ROPE"][Lc:].contiguous()
         ws["ctx_sig"] = None
-        cache_workspace(self._ws, key, ws, device=self.device)
+        cache_workspace(self._ws, key, ws, device=self.device, on_evict=lambda _k: self._graphs.clear())
         return ws
 
     # ------------------------------------------------------------------ schedule
@@ -154,6 +157,24 @@ class ZImageExecutor(nn.Module):
         ops.rmsnorm_modulate(ys, xs, weight=W[name + ".f2"], gate=g_m, residual=xs, eps=eps)
         return 9
 
+    def _prepare_ctx(self, ws, ctx) -> int:
+        """Caption path (RMSNorm + Linear + ``context_refiner`` blocks): a function of the conditioning only, so it
+        runs EAGERLY and only when the conditioning changed - never inside the per-step CUDA graph, which reads the
+        refined caption tokens from the workspace's fixed ``XT0`` buffer."""
+        sig = (ctx.data_ptr(), tuple(ctx.shape), ctx._version)
+        if ws["ctx_sig"] == sig:
+            return 0
+        W, Lc, n = self.W, ws["Lc"], 2
+        XM, Y, ATT, FF = ws["XM"], ws["Y"], ws["ATT"], ws["FF"]
+        ops.rmsnorm_modulate(ctx, ws["CAPN"], weight=W["cap_norm"], eps=self.eps)
+        xt0 = ws["XT0"]
+        ops.gemm(ws["CAPN"], W["cap.w"], "bias", out=xt0, bias=W["cap.b"])
+        for i in range(self.n_cr):
+            n += self._block(ws, f"cr{i}", xt0, XM[:, :Lc], Y[:, :Lc], ATT[:, :Lc], FF[:, :Lc], ws["Qt"], ws["Kt"],
+                             ws["Vt"], ws["ROPE"], False)
+        ws["ctx_sig"] = sig
+        return n
+
     def _run(self, ws, x_ptr: int, t, ctx, out, x_in=None, sigmas=None, out_ptr: Optional[int] = None,
              out_sample_off: int = 0, t_ptr: Optional[int] = None, x_copy=None):
         W, p, Lc = self.W, self.params, ws["Lc"]
@@ -169,17 +190,6 @@ class ZImageExecutor(nn.Module):
         C.silu(ws["TE"], ws["STE"])
         ops.gemm(ws["STE"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])            # every AdaLN vector of the step
         n += 5
-        # caption path: only when the conditioning changed
-        sig = (ctx.data_ptr(), tuple(ctx.shape), ctx._version)
-        if ws["ctx_sig"] != sig:
-            ops.rmsnorm_modulate(ctx, ws["CAPN"], weight=W["cap_norm"], eps=self.eps)
-            xt0 = ws["XT0"]
-            ops.gemm(ws["CAPN"], W["cap.w"], "bias", out=xt0, bias=W["cap.b"])
-            for i in range(self.n_cr):
-                n += self._block(ws, f"cr{i}", xt0, XM[:, :Lc], Y[:, :Lc], ATT[:, :Lc], FF[:, :Lc], ws["Qt"], ws["Kt"],
-                                 ws["Vt"], ws["ROPE"], False)
-            ws["ctx_sig"] = sig
-            n += 2
         C.copy_rows(ws["XT0"], Xt)
         n += 1
         for i in range(self.n_nr):
@@ -214,17 +224,35 @@ class ZImageExecutor(nn.Module):
             B, _, H, Wd = x.shape
             ws = self.workspace(B, H, Wd, context.shape[1])
             out = torch.empty_like(x)
+            self._prepare_ctx(ws, context)
             self._run(ws, x.data_ptr(), timesteps, context, out)
             return out
+
+    def _shard_args(self, x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off):
+        d = self.device
+        timesteps = timesteps.to(device=d, dtype=torch.bfloat16).contiguous()
+        context = context.to(device=d, dtype=torch.bfloat16).contiguous()
+        key = ("shard", tuple(shape), x_src_ptr, timesteps.data_ptr(), context.data_ptr(), tuple(context.shape), out_ptr,
+               out_sample_off)
+        return key, timesteps, context
 
     @torch.no_grad()
     def forward_shard(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int, **_ignored):
         with torch.cuda.device(self.device):
-            d = self.device
-            timesteps = timesteps.to(device=d, dtype=torch.bfloat16).contiguous()
-            context = context.to(device=d, dtype=torch.bfloat16).contiguous()
+            key, timesteps, context = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off)
             ws = self.workspace(shape[0], shape[2], shape[3], context.shape[1])
-            self._run(ws, x_src_ptr, timesteps, context, None, out_ptr=out_ptr, out_sample_off=out_sample_off)
+            self._prepare_ctx(ws, context)
+            self._graphs.run(key, lambda: self._run(ws, x_src_ptr, timesteps, context, None, out_ptr=out_ptr,
+                                                    out_sample_off=out_sample_off))
+
+    def shard_graph_handle(self, x_src_ptr: int, shape, timesteps, context, out_ptr: int, out_sample_off: int,
+                           **_ignored) -> int:
+        with torch.cuda.device(self.device):
+            key, _t, context = self._shard_args(x_src_ptr, shape, timesteps, context, out_ptr, out_sample_off)
+            ws = self.workspace(shape[0], shape[2], shape[3], context.shape[1])
+            if ws["ctx_sig"] != (context.data_ptr(), tuple(context.shape), context._version):
+                return 0                    # conditioning changed: take the Python path once (eager caption path)
+        return self._graphs.exec_handle(key)
 
     @torch.no_grad()
     def denoise_step(self, x, timesteps, context, sigmas, out=None, out_ptr=None, out_sample_off=0,
@@ -234,9 +262,17 @@ class ZImageExecutor(nn.Module):
             ws = self.workspace(B, H, Wd, context.shape[1])
             if out is None and out_ptr is None:
                 out = ws["OUT"]
-            self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, out, x_in=x,
-                      sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
-                      x_copy=x if x_src_ptr is not None else None)
+            self._prepare_ctx(ws, context)
+
+            def body():
+                self._run(ws, x_src_ptr if x_src_ptr is not None else x.data_ptr(), timesteps, context, out, x_in=x,
+                          sigmas=sigmas, out_ptr=out_ptr, out_sample_off=out_sample_off, t_ptr=t_src_ptr,
+                          x_copy=x if x_src_ptr is not None else None)
+
+            key = (tuple(x.shape), x.data_ptr(), timesteps.data_ptr(), context.data_ptr(), tuple(context.shape),
+                   sigmas.data_ptr(), out.data_ptr() if out is not None else 0, out_ptr or 0, out_sample_off,
+                   x_src_ptr or 0, t_src_ptr or 0)
+            self._graphs.run(key, body)
             return out
 
 

@@ -70,6 +70,18 @@ def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     return out.reshape(copad, kh * kw * cpad).contiguous()
 
 
+def pack_conv_in_weight(w: torch.Tensor) -> torch.Tensor:
+    """OIHW 3x3 weight of a UNet's first convolution -> [Cout, 64] bf16, k = tap*Cin + c (tap-major, zero padded):
+    the B operand of the fused scatter + conv_in kernel (csrc/comm/scatter_conv.cu), which builds the matching
+    im2col rows from the lead GPU's NCHW latent."""
+    co, ci, kh, kw = w.shape
+    if (kh, kw) != (3, 3) or 9 * ci > 64:
+        raise ValueError("fused conv_in needs a 3x3 kernel with 9*Cin <= 64")
+    out = torch.zeros(co, 64, dtype=torch.bfloat16, device=w.device)
+    out[:, :9 * ci] = w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.bfloat16)
+    return out.contiguous()
+
+
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, taps: int, stride: int = 1, mode: str = "bias",
                 out: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
     """3x3 (pad 1) or 1x1 convolution on NHWC bf16 as an implicit GEMM on tcgen05 (TMA does the im2col:

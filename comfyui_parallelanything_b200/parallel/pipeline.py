@@ -149,12 +149,17 @@ def wrap_blocks(lead_replica: nn.Module, replicas: Dict[str, nn.Module], device_
             owner_replica = replicas[dev_name]
             peer_list = getattr(owner_replica, name, None)
             owner_block = local_blocks[idx]
-            if owner_replica is not lead_replica and isinstance(peer_list, nn.ModuleList) and idx < len(peer_list):
+            owner_dev = lead_dev
+            if owner_replica is lead_replica:
+                owner_dev = torch.device(dev_name)
+            elif isinstance(peer_list, nn.ModuleList) and idx < len(peer_list):
                 cand = peer_list[idx]
                 while isinstance(cand, PipelineStage):
                     cand = cand.local_block
-                owner_block = cand
-            local_blocks[idx] = PipelineStage(local_blocks[idx], idx, torch.device(dev_name), owner_block,
+                owner_block, owner_dev = cand, torch.device(dev_name)
+            # else: the owner replica exposes no block list (a native executor holds packed weights, not modules):
+            # the stage stays on the lead device with the lead's own block - never a lead block fed foreign tensors.
+            local_blocks[idx] = PipelineStage(local_blocks[idx], idx, owner_dev, owner_block,
                                               idx == len(owners) - 1, lead_dev)
     return assignment
 

@@ -360,7 +360,7 @@ class SpmdUNetEngine(SpmdFluxEngine):
     0's buffer (peer loads), the gather kernel (eps -> Euler -> NCHW) stores into rank 0's output buffer."""
 
     tma_peer_inputs = ("ctx", "y")
-    kernel_pulled_inputs = ("x",)
+    kernel_pulled_inputs = ("x", "t")
 
     def _latent_channels(self) -> int:
         return self.ex.in_ch
@@ -372,19 +372,25 @@ class SpmdUNetEngine(SpmdFluxEngine):
         if m.adm is not None:
             spec["y"] = ((B, m.adm), bf)
         spec["sig"] = ((B, 2), torch.float32)
-        spec["out"] = ((B, self.C, self.H, self.W), bf)
+        spec["out"] = ((B, m.out_ch, self.H, self.W), bf)
         return spec
 
     def _launch(self, loc: dict, fused: bool):
         y = loc.get("y")
         if fused:
             x_bytes = self.C * self.H * self.W * 2
-            # x_in of the Euler update must be local: one small peer copy of the latent shard
+            if getattr(self.ex, "fused_in", False):
+                # fused scatter + conv_in: the first kernel reads the latent shard AND the timesteps from rank 0's heap
+                # and leaves the local NCHW copy (x_in of the Euler gather) in loc["x"] - no separate pull
+                self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"],
+                                     out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
+                                     x_src_ptr=self._src("x", x_bytes), t_src_ptr=self._src("t", 2))
+                return None
             if self.rank != 0:
                 self._pull("x")
+                self._pull("t")
             self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"],
-                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local,
-                                 x_src_ptr=self._src("x", x_bytes))
+                                 out_ptr=self.heap.peer_ptr(0, self.off["out"]), out_sample_off=self.off_local)
             return None
         return self.ex.denoise_step(loc["x"], loc["t"], loc["ctx"], y, loc["sig"])
 

@@ -270,6 +270,28 @@ static void scatter_patch_embed(Tensor W, Tensor bias, uintptr_t x_src, uintptr_
   check(pa::scatter_patch_embed(W.data_ptr(), W.stride(0), p, cur_stream()), "scatter_patch_embed");
 }
 
+static void scatter_conv_in(Tensor W, Tensor bias, uintptr_t x_src, uintptr_t t_src, Tensor t_emb,
+                            c10::optional<Tensor> x_copy, Tensor out, int C, int H, int Wd, double time_factor,
+                            double max_period) {
+  // fused scatter: (peer) NCHW latent shard -> 3x3 im2col -> conv_in GEMM -> NHWC rows, + timestep sinusoid
+  c10::cuda::CUDAGuard guard(out.device());
+  TORCH_CHECK(W.dim() == 2 && W.size(1) == 64 && W.stride(1) == 1, "packed conv_in weight must be [N, 64]");
+  TORCH_CHECK(out.dim() == 3 && out.is_contiguous() && out.size(1) == (int64_t)H * Wd && out.size(2) == W.size(0),
+              "out must be contiguous [n, H*W, N]");
+  TORCH_CHECK(t_emb.dim() == 2 && t_emb.is_contiguous() && t_emb.size(0) == out.size(0), "t_emb must be [n, dim]");
+  pa::ScatterConvParams p{};
+  p.x_src = reinterpret_cast<const __nv_bfloat16*>(x_src);
+  p.t_src = reinterpret_cast<const __nv_bfloat16*>(t_src);
+  p.t_emb = reinterpret_cast<__nv_bfloat16*>(t_emb.data_ptr());
+  p.x_copy = x_copy ? reinterpret_cast<__nv_bfloat16*>(x_copy->data_ptr()) : nullptr;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out.data_ptr());
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(bias.data_ptr());
+  p.n = (int)out.size(0); p.C = C; p.H = H; p.W = Wd; p.N = (int)W.size(0); p.temb_dim = (int)t_emb.size(1);
+  p.time_factor = (float)time_factor;
+  p.max_period = (float)max_period;
+  check(pa::scatter_conv_in(W.data_ptr(), W.stride(0), p, cur_stream()), "scatter_conv_in");
+}
+
 static void nchw_to_nhwc_pad(uintptr_t x_ptr, Tensor out, int B, int C, int HW) {
   c10::cuda::CUDAGuard guard(out.device());
   TORCH_CHECK(out.is_contiguous() && out.size(-1) % 8 == 0);
@@ -441,6 +463,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("timestep_embedding", &timestep_embedding);
   m.def("patchify", &patchify);
   m.def("scatter_patch_embed", &scatter_patch_embed);
+  m.def("scatter_conv_in", &scatter_conv_in);
   m.def("nchw_to_nhwc_pad", &nchw_to_nhwc_pad);
   m.def("upsample2x", &upsample2x);
   m.def("concat_channels", &concat_channels);

@@ -19,3 +19,19 @@ struct ScatterEmbedParams {
 };
 
 }  // namespace pa
+
+namespace pa {
+
+// Fused scatter + first 3x3 convolution (UNet ``conv_in``) + timestep sinusoid.
+struct ScatterConvParams {
+  const __nv_bfloat16* x_src;     // [n, C, H, W] at the lead (peer mapping or local), NCHW
+  const __nv_bfloat16* t_src;     // [n] timesteps at the lead (or local)
+  __nv_bfloat16* t_emb;           // [n, temb_dim]  (cos | sin)
+  __nv_bfloat16* x_copy;          // optional local NCHW copy of the shard (x_in of the Euler gather)
+  __nv_bfloat16* out;             // [n, H*W, N] NHWC rows
+  const __nv_bfloat16* bias;      // [N]
+  int n, C, H, W, N, temb_dim;
+  float time_factor, max_period;
+};
+
+}  // namespace pa

@@ -9,6 +9,8 @@ namespace pa {
 
 struct GemmParams;
 struct ScatterEmbedParams;
+struct ScatterConvParams;
+int scatter_conv_in(const void* W, long long ldw, const ScatterConvParams& p, cudaStream_t st);
 int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& p, cudaStream_t st);
 
 int num_sms();

@@ -42,9 +42,16 @@ def main() -> int:
     rank, world, local = hb.dist_env()
     B = a.batch
     pcts = [100.0 / a.gpus] * a.gpus
-    torch.cuda.set_device(local if a.impl == "ours" or rank else 0)
+    tworld = world
+    if a.impl == "reference":
+        # the reference is one process driving all GPUs: the other torchrun ranks stay off the GPUs (host-only gloo
+        # barrier, no CUDA context / NCCL kernels on the devices its replicas run on) - see bench.py
+        if hb.host_only_group(rank, world):
+            return 0
+        tworld = 1
+    torch.cuda.set_device(local if a.impl == "ours" else 0)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and a.impl == "ours":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     from comfyui_parallelanything_b200.models import wan
@@ -143,13 +150,15 @@ def main() -> int:
     sampler = hb.ClockSampler()
     if rank == 0:
         sampler.start()
-    ms = hb.timed(step_device, a.steps, a.warmup, world)
-    ms_e2e = hb.timed(step_e2e, a.steps, max(1, a.warmup // 2), world)
+    ms = hb.timed(step_device, a.steps, a.warmup, tworld)
+    ms_e2e = hb.timed(step_e2e, a.steps, max(3, a.warmup // 2), tworld)
     clocks = sampler.stop(a.gpus) if rank == 0 else {}
     if eng is not None:
         eng.check_error()
         eng.close()
-    if world > 1:
+    if a.impl == "reference":
+        hb.host_only_release(world)
+    elif world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     if rank == 0:
