@@ -33,6 +33,7 @@ import torch
 import torch.nn as nn
 
 from . import chain as chain_mod
+from . import exec as native_exec
 from .parallel import pipeline as pp
 from .parallel import split as sp
 from .parallel.workers import WorkerPool
@@ -79,6 +80,8 @@ class ParallelEngine:
         self._cond_cache: Dict[Tuple, Any] = {}
         self._lock = threading.Lock()
         self._peer_ready = False
+        self._io: Dict[Tuple, dict] = {}       # fixed staging buffers of the fused path, keyed on shapes + split
+        self._host_exec = None                 # native per-GPU launcher threads (csrc/runtime HostExecutor)
         self.active = False
 
     # ------------------------------------------------------------------ setup
@@ -180,6 +183,7 @@ class ParallelEngine:
             s.worker = self.pool.add(s.device, s.stream)
         self.slots = built
 
+        self._setup_native_runtime()
         if cfg.workload_split and len(built) > 1:
             log.info("Configuring pipeline (layer-split) plan for batch=1")
             pp.wrap_blocks(self.replicas[built[0].name], self.replicas, [s.name for s in built],
@@ -187,12 +191,43 @@ class ParallelEngine:
         self.active = True
         return True
 
+    def _setup_native_runtime(self) -> None:
+        """Peer access between the lead and EVERY native replica (not only the first active set), and one native
+        launcher thread per GPU that replays captured step graphs without the GIL."""
+        native = [s for s in self.slots if getattr(s.replica, "pa_native", False) and s.device.type == "cuda"]
+        if len(native) < 2 or self.slots[0] not in native:
+            self._peer_ready = len(native) == len(self.slots) == 1
+            return
+        from . import ops
+        C = ops.require()
+        lead = self.lead_device.index
+        try:
+            ok = all(C.enable_peer_access(s.device.index, lead) and C.enable_peer_access(lead, s.device.index)
+                     for s in native)
+        except Exception as e:
+            log.warn("peer access could not be enabled (%s); using copy-based scatter/gather", e)
+            ok = False
+        self._peer_ready = bool(ok) and len(native) == len(self.slots)
+        if self._peer_ready and self.config.host_threads and self.config.cuda_graphs:
+            try:
+                self._host_exec = C.HostExecutor([s.device.index for s in self.slots])
+            except Exception as e:
+                log.warn("native launcher threads unavailable (%s); replaying graphs from Python workers", e)
+                self._host_exec = None
+
+    def describe(self) -> dict:
+        """Small JSON-able summary (bench / logs)."""
+        return {"devices": self.device_names, "native": [bool(getattr(s.replica, "pa_native", False)) for s in self.slots],
+                "peer_fused": bool(self._peer_ready), "host_threads": self._host_exec is not None,
+                "graphs": {s.name: len(getattr(s.replica, "_graphs", ())) for s in self.slots
+                           if hasattr(getattr(s.replica, "_graphs", None), "__len__")},
+                "counters": dict(self.metrics.counters)}
+
     def _native_replica(self, dev: torch.device, name: str, index: int):
         """B200 + known model family -> hand-written sm_100a executor packed straight from the
         source weights (device-to-device), instead of a torch replica."""
         if self.config.backend == "torch" or dev.type != "cuda":
             return None
-        from . import exec as native_exec
         build = native_exec.builder_for(self.target)
         if build is None:
             return None
@@ -204,7 +239,7 @@ class ParallelEngine:
             return None
         faults.check_setup(name, index)
         log.info("Building native sm_100a %s executor on %s (free VRAM %.0f MiB)",
-                 getattr(self.target, "pa_family", "?"), name, memory.get_free_vram(name))
+                 native_exec.family_of(self.target) or "?", name, memory.get_free_vram(name))
         return build(self.target, dev, cuda_graphs=self.config.cuda_graphs, fp8=self.config.fp8)
 
     # ------------------------------------------------------------------ forward
@@ -236,8 +271,15 @@ class ParallelEngine:
                 with pp.pipeline_mode(True):
                     lead = self.slots[0]
                     return self._replica_call(lead.replica, x, timesteps, context=context, **kwargs)
-            if batch < n or not self.config.workload_split:
+            if not self.config.workload_split or (batch < n and self.config.small_batch == "lead"):
                 return self._lead_only(x, timesteps, context, kwargs)
+            if batch < n:
+                # The reference runs the lead device alone here (ADP:1308).  With 8 GPUs and a batch of 4 that idles
+                # seven of them, so instead the ``batch`` heaviest devices get one sample each (chain order kept).
+                keep = sorted(sorted(range(n), key=lambda i: (-self.slots[i].weight, i))[:batch])
+                active = [(self.slots[i], 1) for i in keep]
+                self.metrics.incr("small_batch_spread_steps")
+                return self._data_parallel(step, batch, active, x, timesteps, context, kwargs)
             if self.config.pair_cfg and batch % 2 == 0 and batch // 2 >= n:
                 return self._forward_cfg_paired(step, batch, x, timesteps, context, kwargs)
             sizes = self.split_sizes(batch)
@@ -389,66 +431,135 @@ class ParallelEngine:
     def _can_fuse(self, active, x) -> bool:
         if self.config.backend in ("torch", "nccl") or not isinstance(x, torch.Tensor):
             return False
-        if x.device != self.lead_device or x.device.type != "cuda" or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        if x.device != self.lead_device or x.device.type != "cuda" or not x.is_floating_point():
             return False
         if not all(getattr(s.replica, "pa_native", False) and hasattr(s.replica, "forward_shard") for s, _ in active):
             return False
-        if not self._peer_ready:
-            from . import ops
-            C = ops.require()
-            lead = self.lead_device.index
-            ok = all(C.enable_peer_access(s.device.index, lead) for s, _ in active)
-            self._peer_ready = bool(ok)
         return self._peer_ready
 
-    def _data_parallel_fused(self, step, batch, active, offs, x, t_chunks, c_chunks, k_chunks, lead_stream):
-        """Every replica's FIRST kernel loads its latent shard from ``x`` on the lead GPU (NVLink peer loads)
-        and its LAST kernel stores its output rows at their final offset in ``out`` on the lead GPU; the host
-        only orders streams (no copies of x / the result, no cat, no device-wide sync)."""
-        out = torch.empty_like(x)
-        sample_bytes = x[0].numel() * x.element_size()
-        t0 = time.perf_counter()
-
-        # Small per-replica inputs (timesteps, pooled vectors, guidance) are staged from THIS thread before any replica
-        # starts: a cross-device ``.to()`` orders itself after the source device's current stream, so issued from a
-        # worker it can queue behind the lead replica's whole step (measured: 2 GPUs overlapped only ~70 %).
-        staged = []
-        for i, (slot, _size) in enumerate(active):
+    def _io_block(self, active, x, t_chunks, c_chunks, k_chunks) -> dict:
+        """Fixed device buffers for one (shape, split) configuration.  A sampler hands the hooked forward a NEW latent
+        tensor every step (and ComfyUI re-concatenates cond/uncond conditioning every step), while a captured CUDA
+        graph bakes in every pointer: so the step's inputs are staged into these buffers (tiny async copies that also
+        do the dtype conversion) and the replicas' kernels only ever see stable addresses."""
+        def sig(v):
+            return (tuple(v.shape), str(v.dtype)) if isinstance(v, torch.Tensor) else None
+        key = (tuple(x.shape), tuple((s.index, z) for s, z in active), tuple(sig(t) for t in t_chunks),
+               tuple(sig(c) for c in c_chunks), tuple(tuple(sorted((k, sig(v)) for k, v in kc.items())) for kc in k_chunks))
+        io = self._io.get(key)
+        if io is not None:
+            return io
+        lead = self.lead_device
+        bf = torch.bfloat16
+        rep0 = active[0][0].replica
+        out_shape = rep0.out_shape(tuple(x.shape)) if hasattr(rep0, "out_shape") else tuple(x.shape)
+        io = {"x": torch.empty(tuple(x.shape), dtype=bf, device=lead), "out": torch.empty(out_shape, dtype=bf, device=lead),
+              "slots": []}
+        for i, (slot, _z) in enumerate(active):
             dev = slot.device
+
+            def stage(v):
+                if isinstance(v, torch.Tensor) and v.is_floating_point():
+                    return torch.empty(tuple(v.shape), dtype=bf, device=dev)
+                return None
+            io["slots"].append({"t": stage(t_chunks[i]), "ctx": stage(c_chunks[i]), "ctx_src": None,
+                                "kw": {k: stage(v) for k, v in k_chunks[i].items()}})
+        if len(self._io) >= 8:                      # a session walking through many shapes must not pin them all
+            self._io.pop(next(iter(self._io)))
+        self._io[key] = io
+        return io
+
+    def _data_parallel_fused(self, step, batch, active, offs, x, t_chunks, c_chunks, k_chunks, lead_stream):
+        """Every replica's FIRST kernel loads its latent shard from the lead GPU's staging buffer (NVLink peer loads)
+        and its LAST kernel stores its output rows at their final offset in the lead GPU's output buffer; the host only
+        orders streams (no cat, no device-wide sync).  Steps after the second replay ONE CUDA graph per GPU, launched
+        by native host threads (no GIL, no Python in the per-GPU path)."""
+        io = self._io_block(active, x, t_chunks, c_chunks, k_chunks)
+        xs, out = io["x"], io["out"]
+        sample_bytes = xs[0].numel() * xs.element_size()
+        t0 = time.perf_counter()
+        xs.copy_(x, non_blocking=True)                                   # lead stream; also converts fp16/fp32 -> bf16
+
+        # Small per-replica inputs are staged from THIS thread before any replica starts: a cross-device copy orders
+        # itself after the source device's current stream, so issued from a worker it can queue behind the lead
+        # replica's whole step (measured: 2 GPUs overlapped only ~70 %).
+        calls = []
+        for i, (slot, size) in enumerate(active):
+            dev, st = slot.device, io["slots"][i]
             with torch.cuda.device(dev), torch.cuda.stream(slot.stream):
                 slot.stream.wait_stream(lead_stream)
-                t_in = sp.move_to_device(t_chunks[i], dev, non_blocking=True)
-                c_in = self._cached_move(("ctx", i), c_chunks[i], dev)
-                k_in = {k: sp.move_to_device(v, dev, non_blocking=True) for k, v in k_chunks[i].items()}
-            staged.append((t_in, c_in, k_in))
+                t_in = t_chunks[i]
+                if st["t"] is not None:
+                    st["t"].copy_(t_in, non_blocking=True)
+                    t_in = st["t"]
+                c_in = c_chunks[i]
+                if st["ctx"] is not None:
+                    src = c_in
+                    ident = (id(src), src.data_ptr(), src._version)
+                    if not self.config.cache_conditioning or st["ctx_src"] is None or st["ctx_src"][0] != ident:
+                        st["ctx"].copy_(src, non_blocking=True)           # conditioning changed (or first step)
+                        st["ctx_src"] = (ident, src)                      # keep src alive: id/ptr stay unique
+                    else:
+                        self.metrics.incr("cond_cache_hits")
+                    c_in = st["ctx"]
+                k_in = {}
+                for k, v in k_chunks[i].items():
+                    buf = st["kw"].get(k)
+                    if buf is not None:
+                        buf.copy_(v, non_blocking=True)
+                        k_in[k] = buf
+                    else:
+                        k_in[k] = sp.move_to_device(v, dev, non_blocking=True)
+            shape = (size,) + tuple(xs.shape[1:])
+            calls.append((slot, (xs.data_ptr() + offs[i] * sample_bytes, shape, t_in, c_in, out.data_ptr(), offs[i]), k_in))
 
-        def run(i: int):
-            slot, size = active[i]
-            dev = slot.device
-            pp.set_pipeline_mode(False)
-            faults.check_step(step, slot.name, slot.index)
-            t_in, c_in, k_in = staged[i]
-            with torch.cuda.device(dev), torch.cuda.stream(slot.stream):
-                shape = (size,) + tuple(x.shape[1:])
-                slot.replica.forward_shard(x.data_ptr() + offs[i] * sample_bytes, shape, t_in, c_in,
-                                           out.data_ptr(), offs[i], **k_in)
-                lead_stream.wait_stream(slot.stream)
-            return None
+        # ---- replay path: every replica already holds a captured graph for exactly these buffers
+        launched = False
+        if self._host_exec is not None:
+            handles = []
+            for slot, args, k_in in calls:
+                fn = getattr(slot.replica, "shard_graph_handle", None)
+                h = fn(*args, **k_in) if fn is not None else 0
+                if not h:
+                    handles = None
+                    break
+                handles.append(h)
+            if handles is not None:
+                for (slot, _a, _k), h in zip(calls, handles):
+                    faults.check_step(step, slot.name, slot.index)
+                    self._host_exec.launch_graph(slot.index, h, slot.stream.cuda_stream)
+                self._host_exec.sync()                  # launches are enqueued (GIL released); no device sync
+                for slot, _a, _k in calls:
+                    lead_stream.wait_stream(slot.stream)
+                self.metrics.incr("native_graph_steps")
+                launched = True
 
-        futures = [active[i][0].worker.submit(lambda i=i: run(i)) for i in range(len(active))]
-        errors = []
-        for i, f in enumerate(futures):
-            try:
-                f.result()
-            except BaseException as e:  # noqa: BLE001
-                errors.append((active[i][0].name, e))
-        if errors:
-            for name, e in errors:
-                log.error("on %s: %s", name, e)
-            raise errors[0][1]
+        if not launched:
+            def run(i: int):
+                slot, args, k_in = calls[i]
+                pp.set_pipeline_mode(False)
+                faults.check_step(step, slot.name, slot.index)
+                with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream):
+                    slot.replica.forward_shard(*args, **k_in)
+                    lead_stream.wait_stream(slot.stream)
+                return None
+
+            futures = [calls[i][0].worker.submit(lambda i=i: run(i)) for i in range(len(calls))]
+            errors = []
+            for i, f in enumerate(futures):
+                try:
+                    f.result()
+                except BaseException as e:  # noqa: BLE001
+                    errors.append((calls[i][0].name, e))
+            if errors:
+                for name, e in errors:
+                    log.error("on %s: %s", name, e)
+                raise errors[0][1]
         self.metrics.record(step=step, host_ms=(time.perf_counter() - t0) * 1e3, batch=batch,
-                            sizes=[z for _, z in active], fused=True)
-        return out
+                            sizes=[z for _, z in active], fused=True, native_launch=launched)
+        # the sampler may keep every step's result alive: hand back a copy, the fixed buffer is rewritten next step
+        res = out.clone()
+        return res if x.dtype == res.dtype else res.to(x.dtype)
 
     def _cached_move(self, key, value, dev):
         """Conditioning is constant across the steps of one sampling run; re-use the
@@ -499,6 +610,13 @@ class ParallelEngine:
             except Exception:
                 pass
         self.pool.shutdown()
+        if self._host_exec is not None:
+            try:
+                self._host_exec.shutdown()
+            except Exception:
+                pass
+            self._host_exec = None
+        self._io.clear()
         self._cond_cache.clear()
         self._drop_replicas()
         self.slots = []

@@ -20,6 +20,10 @@ Environment variables (all optional):
 ``PA_FLAG_TIMEOUT_MS`` watchdog for in-kernel flag waits (default 20000)
 ``PA_LOG_LEVEL``       python logging level
 ``PA_METRICS_FILE``    JSON-lines metrics sink
+``PA_SMALL_BATCH``     ``spread`` (default: 1 < batch < n_devices uses ``batch`` devices) |
+                       ``lead`` (reference: lead device only)
+``PA_BATCH1``          ``auto`` | ``pipeline`` | ``ulysses`` (batch == 1 mode)
+``PA_HOST_THREADS``    ``1``/``0`` replay per-GPU CUDA graphs from native host threads
 =====================  ========================================================
 """
 from __future__ import annotations
@@ -48,10 +52,21 @@ class EngineConfig:
     fp8: bool = field(default_factory=lambda: _env_bool("PA_FP8", False))   # MXFP8 block GEMMs in native executors
     cache_conditioning: bool = True       # do not re-send constant context every step
     pair_cfg: bool = False                # keep cond/uncond of one sample on one rank
+    # reference semantics for 1 < batch < n_devices is "lead device only" (ADP:1308); by default we instead give one
+    # sample to each of the ``batch`` heaviest devices.  ``PA_SMALL_BATCH=lead`` restores the reference behaviour.
+    small_batch: str = field(default_factory=lambda: os.environ.get("PA_SMALL_BATCH", "spread"))
+    # batch == 1: "pipeline" = the reference's sequential layer split (ADP:1295-1305); "ulysses" = sequence-parallel
+    # attention across the chain's GPUs (native FLUX replicas only; falls back to "pipeline" otherwise)
+    batch1_mode: str = field(default_factory=lambda: os.environ.get("PA_BATCH1", "auto"))
+    host_threads: bool = field(default_factory=lambda: _env_bool("PA_HOST_THREADS", True))   # native graph launcher
 
     def validate(self) -> "EngineConfig":
         if self.split_mode not in ("compat", "exact"):
             raise ValueError(f"split_mode must be compat|exact, got {self.split_mode!r}")
         if self.backend not in ("auto", "fused", "nccl", "torch"):
             raise ValueError(f"backend must be auto|fused|nccl|torch, got {self.backend!r}")
+        if self.small_batch not in ("spread", "lead"):
+            raise ValueError(f"small_batch must be spread|lead, got {self.small_batch!r}")
+        if self.batch1_mode not in ("auto", "pipeline", "ulysses"):
+            raise ValueError(f"batch1_mode must be auto|pipeline|ulysses, got {self.batch1_mode!r}")
         return self

@@ -69,6 +69,8 @@ class Metrics:
     If ``PA_METRICS_FILE`` is set every row is also appended there as JSON.
     """
 
+    MAX_ROWS = 4096          # ring: a long-lived ComfyUI session must not grow this without bound
+
     def __init__(self) -> None:
         self.rows: List[Dict[str, Any]] = []
         self.counters: Dict[str, float] = {}
@@ -83,6 +85,8 @@ class Metrics:
         row.setdefault("ts", time.time())
         with self._lock:
             self.rows.append(row)
+            if len(self.rows) > self.MAX_ROWS:
+                del self.rows[:len(self.rows) - self.MAX_ROWS]
             if self._path:
                 try:
                     with open(self._path, "a") as f:

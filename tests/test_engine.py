@@ -62,7 +62,11 @@ def test_matches_plain_module(B):
 def test_differential_vs_reference(reference):
     base = Toy()
     ours, theirs = copy.deepcopy(base), copy.deepcopy(base)
-    pa.ParallelAnything().setup_parallel(ours, chain_of(40, 40, 15, 5), True, False)
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    # small_batch="lead": the reference's "batch < n_devices -> lead device only" rule (ADP:1308); the default
+    # ("spread") deliberately uses ``batch`` devices instead - covered by test_small_batch_spreads_over_devices
+    pa.ParallelAnything().setup_parallel(ours, chain_of(40, 40, 15, 5), True, False,
+                                         config=EngineConfig(small_batch="lead"))
     reference.ParallelAnything().setup_parallel(theirs, chain_of(40, 40, 15, 5), True, False, True, False)
     for B in (1, 3, 8, 21, 32):
         x, t, c, y = inputs(B)
@@ -76,13 +80,14 @@ def test_differential_vs_reference(reference):
 
 
 def test_mode_thresholds():
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
     m = Toy()
-    pa.ParallelAnything().setup_parallel(m, chain_of(25, 25, 25, 25))
+    pa.ParallelAnything().setup_parallel(m, chain_of(25, 25, 25, 25), config=EngineConfig(small_batch="lead"))
     x, t, c, y = inputs(3)
     m.calls.clear()
     with torch.no_grad():
         m(x, t, context=c)
-    assert m.calls == [3]                      # B < n_devices -> lead only
+    assert m.calls == [3]                      # reference rule (PA_SMALL_BATCH=lead): B < n_devices -> lead only
     x, t, c, y = inputs(4)
     m.calls.clear()
     with torch.no_grad():
@@ -252,3 +257,19 @@ def test_zimage_layers_are_split_in_pipeline_mode_and_batch_split_matches():
             assert torch.allclose(m(**inp), plain(**inp), atol=1e-5)
     pa.cleanup_parallel_model(m)
     assert not isinstance(m.layers[0], pp.PipelineStage)
+
+
+def test_small_batch_spreads_over_devices():
+    """1 < batch < n_devices: the reference idles every device but the lead (ADP:1308); by default we hand one
+    sample to each of the ``batch`` heaviest devices (chain order kept) and still return the plain module's result."""
+    m, plain = Toy(), Toy()
+    plain.load_state_dict(m.state_dict())
+    pa.ParallelAnything().setup_parallel(m, chain_of(40, 40, 15, 5))
+    x, t, c, y = inputs(3)
+    m.calls.clear()
+    with torch.no_grad():
+        got, want = m(x, t, context=c, y=y), plain(x, t, context=c, y=y)
+    assert torch.allclose(got, want, atol=1e-6)
+    assert m.calls == [1, 1, 1]
+    assert m._parallel_engine.metrics.counters.get("small_batch_spread_steps") == 1
+    pa.cleanup_parallel_model(m)

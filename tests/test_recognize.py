@@ -11,7 +11,7 @@ from comfyui_parallelanything_b200 import exec as native_exec
 from comfyui_parallelanything_b200.exec import recognize
 from comfyui_parallelanything_b200.models import flux, unet, vae, wan, zimage
 
-from lookalike import launder
+from comfyui_parallelanything_b200.utils.lookalike import launder
 
 
 def _fields(p):
