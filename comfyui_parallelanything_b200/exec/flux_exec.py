@@ -18,6 +18,7 @@ Per step: 19*13 + 38*4 + ~12 = ~410 kernel launches, optionally replayed as one 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -127,6 +128,9 @@ class FluxExecutor(nn.Module):
         self.n_double, self.n_single = len(model.double_blocks), len(model.single_blocks)
         self._ws: Dict[Tuple, dict] = {}
         self._graphs = GraphCache(self.device, enabled=cuda_graphs)
+        # fork the txt / img chains of the double blocks onto two streams with disjoint SM budgets (PA_DUAL_STREAM=0: off)
+        self.dual_stream = os.environ.get("PA_DUAL_STREAM", "1") != "0"
+        self._side = self._ev_fork = self._ev_join = None
         self.launches_per_step = 0
 
     # nn.Module plumbing so engine utilities (module_device, .to("meta") on cleanup) work
@@ -227,22 +231,58 @@ class FluxExecutor(nn.Module):
         ops.gemm(ws["SVEC"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])            # all modulations
         n += 3
         # ---- double-stream blocks
+        # Between two joint attentions the txt and img chains are independent.  Run back to back, the 512-row txt
+        # GEMMs fill 24-96 of the 74 CTA-pair slots and the img GEMMs end in a partial wave; forked onto two streams
+        # with disjoint SM budgets (share of SMs = share of rows) both chains finish together and every wave is full.
+        dual = self.dual_stream and self.n_double > 0
+        if dual:
+            sms = C.num_sms()
+            txt_sms = min(sms // 2, max(2, int(round(sms * Lt / float(ws["L"]) / 2.0)) * 2))
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+                self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+            side = self._side
+
+        def pre(i, s, xs, xms, seq_off):
+            k = ("d", i, s)
+            ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
+            return 1 + self._lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
+                                 k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
+
+        def post(i, s, xs, xms, a, mh):
+            k = ("d", i, s)
+            m = self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
+            ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 4), shift=self._mod(ws, k, 3))
+            m += self._lin(xms, f"d{i}.{s}.mlp0", "gelu", out=mh)
+            m += self._lin(mh, f"d{i}.{s}.mlp2", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5))
+            return m + 1
+
+        def both(f_img, f_txt):
+            """img chain on the main stream, txt chain on the side stream, disjoint SM budgets; join before returning."""
+            if not dual:
+                return f_img() + f_txt()
+            self._ev_fork.record(main)
+            side.wait_event(self._ev_fork)
+            try:
+                with torch.cuda.stream(side):
+                    C.set_sm_limit(txt_sms)
+                    m = f_txt()
+                    self._ev_join.record(side)
+                C.set_sm_limit(sms - txt_sms)
+                m += f_img()
+            finally:
+                C.set_sm_limit(0)
+            main.wait_event(self._ev_join)
+            return m
+
         for i in range(self.n_double):
           with nvtx_range(f"flux.double[{i}]"):
-            for s, xs, xms, seq_off in (("img", Xi, XMi, Lt), ("txt", Xt, XMt, 0)):
-                k = ("d", i, s)
-                ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
-                n += self._lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
-                               k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
+            n += both(lambda: pre(i, "img", Xi, XMi, Lt), lambda: pre(i, "txt", Xt, XMt, 0))
             ops.attention(Q, K, V, out=ATT)
-            n += 3
-            for s, xs, xms, a, mh in (("img", Xi, XMi, ATT[:, Lt:], MH[:, Lt:]), ("txt", Xt, XMt, ATT[:, :Lt], MH[:, :Lt])):
-                k = ("d", i, s)
-                n += self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
-                ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 4), shift=self._mod(ws, k, 3))
-                n += self._lin(xms, f"d{i}.{s}.mlp0", "gelu", out=mh)
-                n += self._lin(mh, f"d{i}.{s}.mlp2", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5))
-                n += 1
+            n += 1
+            n += both(lambda: post(i, "img", Xi, XMi, ATT[:, Lt:], MH[:, Lt:]),
+                      lambda: post(i, "txt", Xt, XMt, ATT[:, :Lt], MH[:, :Lt]))
         # ---- single-stream blocks
         for i in range(self.n_single):
             k = ("s", i)

@@ -216,7 +216,9 @@ class SpmdFluxEngine:
         n += 1
         if self.n_local > 0:
             if self.rank == 0:
-                loc = {k: self.buf[k][self.off_local:self.off_local + self.n_local] for k in self.input_names}
+                # fresh non-owning views (version counter 0): executors key their cached conditioning work on
+                # (pointer, shape, version); a slice of ``self.buf`` would bump its version on every ``stage_inputs``
+                loc = {k: self._peer_view(k) for k in self.input_names}
             else:
                 loc = {k: v[:self.n_local] for k, v in self.loc.items()}
                 for name in self.input_names:

@@ -879,23 +879,35 @@ def unet_executor_graph_replay():
     ex = UNetExecutor(m, _dev(), cuda_graphs=True)
     inp = unet.example_inputs(cfg, 2, 256, 256, ctx_len=77, device=_dev(), dtype=torch.bfloat16)
     sig = torch.tensor([[14.6, 10.0], [14.6, 10.0]], device=_dev())
-    ref = UNetExecutor(m, _dev(), cuda_graphs=False)
-    ok, worst = True, 0.0
+    ref, ref2 = UNetExecutor(m, _dev(), cuda_graphs=False), UNetExecutor(m, _dev(), cuda_graphs=False)
+    ok, worst, floor, drift = True, 0.0, 0.0, 0.0
+    prev = None
     for it in range(5):
         inp["x"].mul_(0.9)
         if it == 3:
             inp["context"].mul_(-1.0)                       # new prompt, same buffer
-            ex.invalidate_conditioning()
-            ref.invalidate_conditioning()
+            for e_ in (ex, ref, ref2):
+                e_.invalidate_conditioning()
         got = ex.denoise_step(inp["x"], inp["timesteps"], inp["context"], inp["y"], sig).clone()
         want = ref.denoise_step(inp["x"], inp["timesteps"], inp["context"], inp["y"], sig).clone()
+        again = ref2.denoise_step(inp["x"], inp["timesteps"], inp["context"], inp["y"], sig).clone()
         torch.cuda.synchronize()
-        d = (got.float() - want.float()).abs().max().item()
-        worst = max(worst, d)
-        ok = ok and d == 0.0
+        scale = want.float().abs().mean().item() + 1e-6
+        # GroupNorm statistics are reduced with fp32 atomics (order varies run to run), so two EAGER executions only
+        # agree to a noise floor, measured here; the graph replay must sit within it.  A replay that missed the in-place
+        # input change / the new prompt would be off by about the step-to-step drift instead.
+        d = (got.float() - want.float()).abs().mean().item() / scale
+        nf = (again.float() - want.float()).abs().mean().item() / scale
+        if prev is not None:
+            drift = max(drift, (want.float() - prev).abs().mean().item() / scale)
+        prev = want.float()
+        worst, floor = max(worst, d), max(floor, nf)
+        ok = ok and d <= 4.0 * nf + 2e-3
+    ok = ok and drift > 10.0 * worst
     return dict(name="unet_executor_graph_replay", ok=bool(ok and len(ex._graphs) == 1 and ex._graphs.replays >= 3
                                                           and ex.fused_in),
-                max_abs=worst, captured=len(ex._graphs), replays=ex._graphs.replays, fused_conv_in=bool(ex.fused_in),
+                mean_rel_graph_vs_eager=worst, mean_rel_eager_vs_eager=floor, step_to_step_drift=drift,
+                captured=len(ex._graphs), replays=ex._graphs.replays, fused_conv_in=bool(ex.fused_in),
                 launches=ex.launches_per_step)
 
 

@@ -486,6 +486,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("signal_flags", &signal_flags);
   m.def("wait_flags", &wait_flags);
   m.def("num_sms", &pa::num_sms);
+  m.def("set_sm_limit", &pa::set_sm_limit);
   pa::rt::bind(m);
   m.attr("EPI_BIAS") = (int)pa::EPI_BIAS;
   m.attr("EPI_BIAS_GELU") = (int)pa::EPI_BIAS_GELU;

@@ -14,6 +14,7 @@ int scatter_conv_in(const void* W, long long ldw, const ScatterConvParams& p, cu
 int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& p, cudaStream_t st);
 
 int num_sms();
+void set_sm_limit(int n);   // per-thread SM budget for persistent-kernel grids (0 = all)
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int elem_bytes, const uint32_t* elem_strides = nullptr);
 int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int taps, int stride, GemmParams p,

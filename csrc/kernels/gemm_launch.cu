@@ -50,12 +50,26 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
   return 0;
 }
 
-int num_sms() {
+// SM budget of the calling thread (0 = whole device).  Two independent kernel chains (FLUX's txt and img streams
+// between two attention calls) run CONCURRENTLY on disjoint SM sets when each persistent kernel is launched with
+// only its share of the SMs: 8 CTA pairs for the 512-row txt GEMMs + 66 pairs for the 4096-row img GEMMs finish in 3
+// waves where the same two GEMMs back to back take 3 + 1 (profiles/README.md "txt/img SM partition").
+static thread_local int g_sm_limit = 0;
+
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
+static int real_sms() {
   static int n[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
   return n[dev];
+}
+
+int num_sms() {
+  const int real = real_sms();
+  if (g_sm_limit > 0 && g_sm_limit < real) return g_sm_limit & ~1;      // whole CTA pairs (TPCs)
+  return real;
 }
 
 // Widest tile that (a) divides N without a ragged last tile where possible and (b) still yields at least one

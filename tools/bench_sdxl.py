@@ -66,7 +66,7 @@ def main() -> int:
         from comfyui_parallelanything_b200.exec.unet_exec import UNetExecutor
         torch.manual_seed(1234)
         model = unet.UNetModel(**cfg).to(device=dev, dtype=torch.bfloat16).eval()
-        ex = UNetExecutor(model, dev)
+        ex = UNetExecutor(model, dev, cuda_graphs=True)
         del model
         if world == 1:
             d = {k: v.to(dev) for k, v in host.items()}

@@ -66,7 +66,7 @@ def main() -> int:
         torch.manual_seed(1234)
         with torch.device(dev):
             model = wan.WanModel(cfg, dtype=torch.bfloat16).eval()
-        ex = WanExecutor(model, dev)
+        ex = WanExecutor(model, dev, cuda_graphs=True)
         del model
         torch.cuda.empty_cache()
         if world == 1:

@@ -69,7 +69,7 @@ def main() -> int:
         torch.manual_seed(1234)
         with torch.device(dev):
             model = zimage.ZImageModel(cfg, dtype=torch.bfloat16).eval()
-        ex = ZImageExecutor(model, dev)
+        ex = ZImageExecutor(model, dev, cuda_graphs=True)
         del model
         torch.cuda.empty_cache()
         if world == 1:

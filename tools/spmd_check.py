@@ -29,7 +29,7 @@ def main() -> int:
                         mlp_ratio=4.0, num_heads=4, depth=2, depth_single_blocks=2)
     torch.manual_seed(5)
     model = flux.Flux(p).to(device=dev, dtype=torch.bfloat16).eval()
-    ex = FluxExecutor(model, dev)
+    ex = FluxExecutor(model, dev, cuda_graphs=True)
     B, H, W, Lt = 5 if world == 2 else 2 * world + 1, 256, 384, 77
     inp = flux.example_inputs(p, B, H, W, txt_len=Lt, device=dev, dtype=torch.bfloat16, seed=11)
     sig = torch.tensor([[1.0 - 0.1 * i, 0.8 - 0.1 * i] for i in range(B)], device=dev)
@@ -40,7 +40,7 @@ def main() -> int:
         os.environ["PA_TMA_PEER"] = tma_peer
         weights = [60, 40][:world] if world == 2 else None
         eng = SpmdFluxEngine(ex, B, H, W, Lt, weights=weights, backend=backend)
-        for it in range(3):                                     # several epochs: flag reuse
+        for it in range(4):                                     # several epochs: flag reuse; eager, capture, replay x2
             if rank == 0:
                 eng.stage_inputs(inp["x"], inp["timesteps"], inp["context"], inp["y"], inp["guidance"], sig)
             out = eng.step()
@@ -70,7 +70,7 @@ def other_family(family, rank, world, dev) -> int:
         from comfyui_parallelanything_b200.models import unet
         cfg = unet.mini_sdxl_config()
         torch.manual_seed(3)
-        ex = UNetExecutor(unet.UNetModel(**cfg).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        ex = UNetExecutor(unet.UNetModel(**cfg).to(device=dev, dtype=torch.bfloat16).eval(), dev, cuda_graphs=True)
         inp = unet.example_inputs(cfg, B, 256, 384, ctx_len=77, device=dev, dtype=torch.bfloat16)
         order = [inp["x"], inp["timesteps"], inp["context"], inp["y"], sig]
         want = ex.denoise_step(*order).clone()
@@ -80,7 +80,7 @@ def other_family(family, rank, world, dev) -> int:
         from comfyui_parallelanything_b200.models import zimage
         p = zimage.zimage_tiny_params()
         torch.manual_seed(4)
-        ex = ZImageExecutor(zimage.ZImageModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        ex = ZImageExecutor(zimage.ZImageModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev, cuda_graphs=True)
         inp = zimage.example_inputs(p, B, 256, 384, cap_len=40, device=dev, dtype=torch.bfloat16)
         x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
         order = [x, t, c, sig]
@@ -91,7 +91,7 @@ def other_family(family, rank, world, dev) -> int:
         from comfyui_parallelanything_b200.models import wan
         p = wan.wan_tiny_params()
         torch.manual_seed(2)
-        ex = WanExecutor(wan.WanModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev)
+        ex = WanExecutor(wan.WanModel(p).to(device=dev, dtype=torch.bfloat16).eval(), dev, cuda_graphs=True)
         inp = wan.example_inputs(p, B, frames=8, height=128, width=192, device=dev, dtype=torch.bfloat16)
         x, t, c = ex._prep(inp["x"], inp["timesteps"], inp["context"])
         order = [x, t, c, sig]
@@ -102,7 +102,7 @@ def other_family(family, rank, world, dev) -> int:
     for backend, tma_peer in (("fused", "1"), ("fused", "0"), ("nccl", "0")):
         os.environ["PA_TMA_PEER"] = tma_peer
         eng = make(backend, [60, 40][:world] if world == 2 else None)
-        for it in range(3):
+        for it in range(4):
             if rank == 0:
                 eng.stage_inputs(*order)
             out = eng.step()
