@@ -230,22 +230,13 @@ DTYPE_NAMES = {"bf16": "bf16", "fp8": "fp8 (MXFP8 block-scaled tcgen05 GEMMs for
 
 
 # ----------------------------------------------------------------------------- our arm (one process per GPU)
-def run_ours(args) -> int:
+def measure_ours(args, dtype: str, rank: int, world: int, dev, host, params, with_clocks: bool) -> dict:
+    """Build the executor (+ SPMD engine) for ``dtype``, time the device step and the end-to-end step, verify the
+    multi-GPU result against the single-GPU executor, tear everything down.  Returns the measured fields."""
     import torch
-    rank, world, local = dist_env()
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    from comfyui_parallelanything_b200 import ops
     from comfyui_parallelanything_b200.exec.flux_exec import FluxExecutor
     from comfyui_parallelanything_b200.models import flux
-    ops.require()
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    params, host = synthetic_inputs(B, pinned=True)
     t_setup = time.perf_counter()
     setup = {}
     if world > 1 and args.replicate != "seed":
@@ -255,7 +246,7 @@ def run_ours(args) -> int:
         torch.manual_seed(1234 if rank == 0 else 99)
         with torch.device(dev):
             model = flux.Flux(params, dtype=torch.bfloat16)
-        ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
+        ex = FluxExecutor(model, dev, fp8=(dtype == "fp8"), cuda_graphs=not args.no_graphs)
         del model
         torch.cuda.synchronize()
         setup = replicate_nvl.broadcast_executor(ex, src=0, method=args.replicate)
@@ -263,14 +254,15 @@ def run_ours(args) -> int:
         torch.manual_seed(1234)                          # identical random-init weights on every rank
         with torch.device(dev):
             model = flux.Flux(params, dtype=torch.bfloat16)
-        ex = FluxExecutor(model, dev, fp8=(args.dtype == "fp8"), cuda_graphs=not args.no_graphs)
+        ex = FluxExecutor(model, dev, fp8=(dtype == "fp8"), cuda_graphs=not args.no_graphs)
         del model
     torch.cuda.empty_cache()
     torch.cuda.synchronize()
     setup["setup_s"] = round(time.perf_counter() - t_setup, 2)
 
     result_host = torch.empty(B, 16, 128, 128, dtype=torch.bfloat16).pin_memory()
-    extra = {"setup": setup}
+    res = {"setup": setup}
+    eng = None
     if world == 1:
         d = {k: v.to(dev) for k, v in host.items()}
         xs = ex._prep(d["x"], d["timesteps"], d["context"], d["y"], d["guidance"])
@@ -286,8 +278,8 @@ def run_ours(args) -> int:
             ex.denoise_step(stage["x"], stage["timesteps"], stage["context"], stage["y"], stage["guidance"],
                             stage["sig"], out=out_buf)
             result_host.copy_(out_buf, non_blocking=True)
-        notes = {"parallelism": "one GPU, one CUDA graph per step",
-                 "step": "model forward + Euler update (fused into the last GEMM epilogue)"}
+        res["notes"] = {"parallelism": "one GPU, one CUDA graph per step",
+                        "step": "model forward + Euler update (fused into the last GEMM epilogue)"}
     else:
         from comfyui_parallelanything_b200.parallel.spmd import SpmdFluxEngine
         eng = SpmdFluxEngine(ex, B, 1024, 1024, 512, backend=args.backend)
@@ -305,21 +297,19 @@ def run_ours(args) -> int:
             out = eng.step()
             if rank == 0:
                 result_host.copy_(out, non_blocking=True)
-        notes = {"parallelism": (f"one process per GPU ({args.backend}: in-kernel NVLink scatter/gather)"
-                                 if args.backend == "fused" else "one process per GPU (NCCL send/recv baseline)"),
-                 "step": "model forward + Euler update (fused into the last GEMM epilogue, peer stores to rank 0)"}
+        res["notes"] = {"parallelism": (f"one process per GPU ({args.backend}: in-kernel NVLink scatter/gather)"
+                                        if args.backend == "fused" else "one process per GPU (NCCL send/recv baseline)"),
+                        "step": "model forward + Euler update (fused into the last GEMM epilogue, peer stores to rank 0)"}
 
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = result_host.numel() * result_host.element_size()
     sampler = ClockSampler()
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
-    ms = timed(step_device, args.steps, args.warmup, world)
-    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), world)
-    clocks = sampler.stop(args.gpus) if rank == 0 else {}
+    res["ms"] = timed(step_device, args.steps, args.warmup, world)
+    res["ms_e2e"] = timed(step_e2e, args.steps, max(3, args.warmup // 2), world)
+    res["clocks"] = sampler.stop(args.gpus) if (rank == 0 and with_clocks) else {}
     if world > 1:
         eng.check_error()
-        launches = eng.comm_launches * args.steps
+        res["launches"] = eng.comm_launches * args.steps
         # correctness of the multi-GPU result: one more SPMD step, then rank 0 recomputes the WHOLE batch on its own
         # single-GPU executor from the same staged inputs and compares with the gathered output.
         out = eng.step()
@@ -329,18 +319,54 @@ def run_ours(args) -> int:
             b = eng.buf
             want = ex.denoise_step(b["x"], b["t"], b["ctx"], b["y"], b["g"], b["sig"]).clone()
             torch.cuda.synchronize()
-            extra["output_matches_n1"] = rel_err(got, want)
+            res["output_matches_n1"] = rel_err(got, want)
+            res["result"] = got
         barrier_sync(world)
     else:
-        launches = ex.launches_per_step * args.steps
-    finite = bool(torch.isfinite(result_host.float()).all().item()) if rank == 0 else True
-    if world > 1:
+        res["launches"] = ex.launches_per_step * args.steps
+        res["result"] = out_buf.clone()
+    res["finite"] = bool(torch.isfinite(result_host.float()).all().item()) if rank == 0 else True
+    if eng is not None:
         eng.close()
+    ex.release()
+    del ex
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args) -> int:
+    import torch
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    from comfyui_parallelanything_b200 import ops
+    ops.require()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    params, host = synthetic_inputs(args.batch, pinned=True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = args.batch * 16 * 128 * 128 * 2
+    main = measure_ours(args, args.dtype, rank, world, dev, host, params, with_clocks=True)
+    extra = {"setup": main["setup"]}
+    if "output_matches_n1" in main:
+        extra["output_matches_n1"] = main["output_matches_n1"]
+    if args.dtype == "fp8" and not args.no_bf16:
+        # BASELINE config 3 names fp8, so the headline is the MXFP8 engine; the same workload in bf16 (the precision of
+        # the reference arm) is measured in the same run so both comparisons can be read off one line.
+        alt = measure_ours(args, "bf16", rank, world, dev, host, params, with_clocks=False)
+        if rank == 0:
+            extra["bf16"] = {"value": round(1000.0 / alt["ms"], 4), "unit": "steps/s", "ms_per_step": round(alt["ms"], 3),
+                             "e2e_ms_per_step": round(alt["ms_e2e"], 3), "e2e_value": round(1000.0 / alt["ms_e2e"], 4)}
+            extra["fp8_vs_bf16_output"] = rel_err(main["result"], alt["result"])
+    if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
     if rank == 0:
-        emit(make_line(args, "ours", ms, ms_e2e, clocks, h2d, d2h, launches, finite, DTYPE_NAMES[args.dtype], notes,
-                       extra))
+        emit(make_line(args, "ours", main["ms"], main["ms_e2e"], main["clocks"], h2d, d2h, main["launches"],
+                       main["finite"], DTYPE_NAMES[args.dtype], main["notes"], extra))
     return 0
 
 
@@ -547,8 +573,10 @@ def main() -> int:
                     help="N>1: how ranks != 0 get their weights: same RNG seed (default), NVSwitch multicast kernel, "
                          "or NCCL broadcast of the packed executor weights from rank 0")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--dtype", default=os.environ.get("PA_BENCH_DTYPE", "bf16"), choices=["bf16", "fp8"],
-                    help="fp8 = MXFP8 block-scaled block GEMMs (BASELINE config 3 names fp8)")
+    ap.add_argument("--dtype", default=os.environ.get("PA_BENCH_DTYPE", "fp8"), choices=["bf16", "fp8"],
+                    help="fp8 (default; BASELINE config 3 names fp8) = MXFP8 block-scaled GEMMs for the block linears; "
+                         "the bf16 number of the same workload is measured in the same run and reported under 'bf16'")
+    ap.add_argument("--no-bf16", action="store_true", help="with --dtype fp8: skip the additional bf16 measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     quiet_stdout()

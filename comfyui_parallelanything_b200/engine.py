@@ -81,6 +81,9 @@ class ParallelEngine:
         self._lock = threading.Lock()
         self._peer_ready = False
         self._io: Dict[Tuple, dict] = {}       # fixed staging buffers of the fused path, keyed on shapes + split
+        self._native_src = None                # first native executor built from the module: source of the replication
+        self._native_shells: List[Any] = []    # executors of the same geometry on other GPUs, filled over NVLink
+        self.setup_report: Dict[str, Any] = {}
         self._host_exec = None                 # native per-GPU launcher threads (csrc/runtime HostExecutor)
         self.active = False
 
@@ -183,6 +186,19 @@ class ParallelEngine:
             s.worker = self.pool.add(s.device, s.stream)
         self.slots = built
 
+        shells = [sh for sh in self._native_shells if any(s.replica is sh for s in built)]
+        if shells and self._native_src is not None:
+            from .parallel import replicate_nvl
+            try:
+                rep = replicate_nvl.replicate_inprocess(self._native_src, shells, method=self.config.replicate)
+            except Exception as e:
+                log.error("Weight replication over NVLink failed: %s", e)
+                self._drop_replicas()
+                return False
+            self.setup_report["replication"] = rep
+            log.info("Replicated %.1f GB of packed weights to %d GPU(s) via %s in %.3f s (%.0f GB/s)",
+                     rep["bytes"] / 1e9, rep["receivers"], rep["method"], rep["seconds"], rep["gbps"])
+        self._native_shells = []
         self._setup_native_runtime()
         if cfg.workload_split and len(built) > 1:
             log.info("Configuring pipeline (layer-split) plan for batch=1")
@@ -221,7 +237,7 @@ class ParallelEngine:
                 "peer_fused": bool(self._peer_ready), "host_threads": self._host_exec is not None,
                 "graphs": {s.name: len(getattr(s.replica, "_graphs", ())) for s in self.slots
                            if hasattr(getattr(s.replica, "_graphs", None), "__len__")},
-                "counters": dict(self.metrics.counters)}
+                "counters": dict(self.metrics.counters), "setup": dict(self.setup_report)}
 
     def _native_replica(self, dev: torch.device, name: str, index: int):
         """B200 + known model family -> hand-written sm_100a executor packed straight from the
@@ -238,9 +254,21 @@ class ParallelEngine:
                                    f"{ops.load_error()!r}")
             return None
         faults.check_setup(name, index)
+        if self._native_src is not None and self.config.replicate != "rebuild":
+            # The packed weights already exist on another GPU: allocate an executor of the same geometry here and fill
+            # it device-to-device afterwards (NVSwitch multicast kernel, or peer copies) instead of re-packing /
+            # re-quantising from the torch module once per device (reference: CPU bounce per device, ADP:600-663).
+            from .parallel import replicate_nvl
+            log.info("Allocating native %s replica on %s (free VRAM %.0f MiB); weights arrive over NVLink",
+                     native_exec.family_of(self.target) or "?", name, memory.get_free_vram(name))
+            shell = replicate_nvl.shell_like(self._native_src, dev)
+            self._native_shells.append(shell)
+            return shell
         log.info("Building native sm_100a %s executor on %s (free VRAM %.0f MiB)",
                  native_exec.family_of(self.target) or "?", name, memory.get_free_vram(name))
-        return build(self.target, dev, cuda_graphs=self.config.cuda_graphs, fp8=self.config.fp8)
+        ex = build(self.target, dev, cuda_graphs=self.config.cuda_graphs, fp8=self.config.fp8)
+        self._native_src = ex
+        return ex
 
     # ------------------------------------------------------------------ forward
     def _replica_call(self, replica: nn.Module, *a, **k):

@@ -23,6 +23,7 @@ Environment variables (all optional):
 ``PA_SMALL_BATCH``     ``spread`` (default: 1 < batch < n_devices uses ``batch`` devices) |
                        ``lead`` (reference: lead device only)
 ``PA_BATCH1``          ``auto`` | ``pipeline`` | ``ulysses`` (batch == 1 mode)
+``PA_REPLICATE``       ``auto`` | ``nvls`` | ``p2p`` | ``rebuild``: how further GPUs get the packed weights
 ``PA_HOST_THREADS``    ``1``/``0`` replay per-GPU CUDA graphs from native host threads
 =====================  ========================================================
 """
@@ -58,6 +59,9 @@ class EngineConfig:
     # batch == 1: "pipeline" = the reference's sequential layer split (ADP:1295-1305); "ulysses" = sequence-parallel
     # attention across the chain's GPUs (native FLUX replicas only; falls back to "pipeline" otherwise)
     batch1_mode: str = field(default_factory=lambda: os.environ.get("PA_BATCH1", "auto"))
+    # how replicas on further GPUs get their packed weights: "auto" (NVSwitch multicast kernel if the fabric supports
+    # it, else peer copies) | "nvls" | "p2p" | "rebuild" (pack again from the torch module on every device)
+    replicate: str = field(default_factory=lambda: os.environ.get("PA_REPLICATE", "auto"))
     host_threads: bool = field(default_factory=lambda: _env_bool("PA_HOST_THREADS", True))   # native graph launcher
 
     def validate(self) -> "EngineConfig":
@@ -65,6 +69,8 @@ class EngineConfig:
             raise ValueError(f"split_mode must be compat|exact, got {self.split_mode!r}")
         if self.backend not in ("auto", "fused", "nccl", "torch"):
             raise ValueError(f"backend must be auto|fused|nccl|torch, got {self.backend!r}")
+        if self.replicate not in ("auto", "nvls", "p2p", "rebuild"):
+            raise ValueError(f"replicate must be auto|nvls|p2p|rebuild, got {self.replicate!r}")
         if self.small_batch not in ("spread", "lead"):
             raise ValueError(f"small_batch must be spread|lead, got {self.small_batch!r}")
         if self.batch1_mode not in ("auto", "pipeline", "ulysses"):

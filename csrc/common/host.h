@@ -13,6 +13,7 @@ struct ScatterConvParams;
 int scatter_conv_in(const void* W, long long ldw, const ScatterConvParams& p, cudaStream_t st);
 int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& p, cudaStream_t st);
 
+int multimem_bcast(const void* src, void* mc_dst, long long bytes, cudaStream_t st);
 int num_sms();
 void set_sm_limit(int n);   // per-thread SM budget for persistent-kernel grids (0 = all)
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -194,7 +194,10 @@ class HostExecutor {
   std::vector<std::unique_ptr<Worker>> workers_;
 };
 
+void bind_multicast(py::module_& m);
+
 void bind(py::module_& m) {
+  bind_multicast(m);
   m.def("can_access_peer", &can_access_peer);
   m.def("enable_peer_access", &enable_peer_access);
   m.def("dev_malloc", &dev_malloc, py::arg("device"), py::arg("bytes"), py::arg("zero") = true);

@@ -70,6 +70,41 @@ def test_multi_gpu_fused_dp_matches_single():
     rel, eng = _flux_case(devs, batch=2 * n + 1)
     assert rel < 0.03, rel
     assert any(r.get("fused") for r in eng.metrics.rows), "fused in-process path was not taken"
+    # replicas 1.. were filled over NVLink from the lead's packed weights (multicast kernel or peer copies), not re-packed
+    rep = eng.setup_report.get("replication")
+    assert rep and rep["method"] in ("nvls", "p2p") and rep["receivers"] == n - 1, rep
+    assert eng.metrics.counters.get("native_graph_steps", 0) >= 1, "graphs were not replayed by the native host threads"
+
+
+@pytest.mark.multigpu
+def test_fresh_tensors_every_step_still_replay_graphs():
+    """A sampler hands the hooked forward NEW tensors every step (and ComfyUI re-concatenates the conditioning): the
+    engine stages them into fixed buffers, so every replica keeps replaying ONE captured graph."""
+    devs = [f"cuda:{i}" for i in range(2)]
+    torch.manual_seed(0)
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=512,
+                        mlp_ratio=4.0, num_heads=4, depth=1, depth_single_blocks=2)
+    m = flux.Flux(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    pa.ParallelAnything().setup_parallel(m, _chain(devs))
+    eng = m._parallel_engine
+    base = flux.example_inputs(p, 4, 256, 256, txt_len=64, device=devs[0], dtype=torch.bfloat16)
+    outs = []
+    with torch.no_grad():
+        for it in range(6):
+            inp = {k: (v * (1.0 - 0.05 * it)).clone() if k == "x" else v.clone() for k, v in base.items()}   # all fresh
+            got = m(inp["x"], inp["timesteps"], context=inp["context"], y=inp["y"], guidance=inp["guidance"])
+            outs.append((inp, got))
+        torch.cuda.synchronize()
+        for inp, got in outs[-2:]:
+            want = oracle(**{k: v.float() for k, v in inp.items()})
+            rel = (got.float() - want).abs().mean().item() / want.abs().mean().item()
+            assert rel < 0.03, rel
+    assert not torch.equal(outs[-1][1], outs[-2][1])              # results were not overwritten by later steps
+    graphs = {n_: len(r._graphs) for n_, r in eng.replicas.items()}
+    assert all(v == 1 for v in graphs.values()), graphs
+    assert eng.metrics.counters.get("native_graph_steps", 0) >= 3
+    pa.cleanup_parallel_model(m)
 
 
 @pytest.mark.multigpu

@@ -24,3 +24,17 @@ def test_spmd_fused_matches_single_gpu(family):
     assert res["ok"] and res["world"] == n, res
     for name, v in res["results"].items():
         assert v["mean_rel"] < 5e-3, (name, v)
+
+
+def test_spmd_weight_broadcast_nvls_or_nccl():
+    """K9: packed executor weights from rank 0 to every rank (multimem.st through an NVSwitch multicast object shared via
+    POSIX fds; NCCL broadcast when the fabric has no multicast) - all ranks must end up with rank 0's bytes."""
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29537", os.path.join(ROOT, "tools", "spmd_check.py"), "bcast"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("PA_SPMD ")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1][len("PA_SPMD "):])
+    assert res["ok"] and res["world"] == n, res
+    print("weight broadcast:", {k: (v["method"], v.get("gbps"), v.get("why_not_nvls")) for k, v in res["results"].items()})

@@ -140,3 +140,57 @@ def test_packed_weight_checkpoint_roundtrip_and_mismatch(tmp_path):
         pack_cache.load_packed_into(shp, path)                           # shape mismatch
     with pytest.raises(TypeError):
         pack_cache.save_packed(object(), path)                           # no packed table
+
+
+def test_executor_shell_clone_structure_and_p2p_fill():
+    """parallel/replicate_nvl.shell_like: the receive side of a weight replication - same packed-table keys / shapes on
+    the target device, fresh runtime state, aliasing between the flat block list and the layer tree preserved."""
+    import torch
+    import torch.nn as nn
+    from types import SimpleNamespace
+    from comfyui_parallelanything_b200.exec.graphs import GraphCache
+    from comfyui_parallelanything_b200.exec.pack_cache import packed_table
+    from comfyui_parallelanything_b200.parallel import replicate_nvl
+
+    class Blk:
+        def __init__(self, i):
+            self.w = torch.full((4, 4), float(i))
+            self.heads = 2
+            self._kv = torch.zeros(3)
+            self._kv_sig = ("x",)
+
+    class FakeExec(nn.Module):
+        pa_native = True
+
+        def __init__(self):
+            super().__init__()
+            self.device = torch.device("cpu")
+            self.params = SimpleNamespace(dim=8, axes=[1, 2])
+            self.inp = [[("st", Blk(1))], [("st", Blk(2))]]
+            self._tblocks = [self.inp[0][0][1], self.inp[1][0][1]]
+            self.emb_w = torch.arange(6.0)
+            self._graphs = GraphCache("cpu", enabled=False)
+            self._io = {"k": 1}
+            self.launches_per_step = 7
+
+    src = FakeExec()
+    sh = replicate_nvl.shell_like(src, "cpu")
+    assert type(sh) is FakeExec and sh is not src and sh.launches_per_step == 7 and sh._io == {}
+    assert sh.params.dim == 8 and sh.params is not src.params and sh._graphs is not src._graphs
+    assert sh._tblocks[0] is sh.inp[0][0][1] and sh._tblocks[1] is sh.inp[1][0][1]          # aliasing preserved
+    assert sh._tblocks[0]._kv is None and sh._tblocks[0]._kv_sig is None and sh._tblocks[0].heads == 2
+    ts, td = packed_table(src), packed_table(sh)
+    assert list(ts) == list(td) and all(td[k].shape == ts[k].shape and td[k] is not ts[k] for k in ts)
+    pairs = replicate_nvl._pairs(src, [sh])
+    for s_, ds in pairs:
+        ds[0].copy_(s_)
+    assert all(torch.equal(td[k], ts[k]) for k in ts)
+    # chunk packing: every byte of every tensor exactly once, offsets aligned, slots never overflow
+    big = [(torch.empty(1000, dtype=torch.uint8), []), (torch.empty(70000, dtype=torch.uint8), []),
+           (torch.empty(16, dtype=torch.uint8), [])]
+    seen = {0: 0, 1: 0, 2: 0}
+    for chunk in replicate_nvl._chunks(big, 32768):
+        for idx, pos, take, off in chunk:
+            assert off % 256 == 0 and off + take <= 32768 and pos == seen[idx]
+            seen[idx] += take
+    assert seen == {0: 1000, 1: 70000, 2: 16}

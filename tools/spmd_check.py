@@ -20,6 +20,8 @@ def main() -> int:
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     family = sys.argv[1] if len(sys.argv) > 1 else "flux"
+    if family == "bcast":
+        return bcast_check(rank, world, dev)
     if family != "flux":
         return other_family(family, rank, world, dev)
     from comfyui_parallelanything_b200.exec.flux_exec import FluxExecutor
@@ -54,6 +56,41 @@ def main() -> int:
     if rank == 0:
         ok = all(v["mean_rel"] < 5e-3 for v in res.values())
         print("PA_SPMD " + json.dumps(dict(world=world, ok=ok, results=res)), flush=True)
+    dist.destroy_process_group()
+    return 0
+
+
+def bcast_check(rank, world, dev) -> int:
+    """Weight replication for the one-process-per-GPU layout: every rank packs an executor from DIFFERENT random
+    weights, rank 0 broadcasts its packed table (NVSwitch multicast kernel, NCCL fallback), and afterwards every rank
+    must hold rank 0's bytes (fp64 checksums + first/last bytes of every tensor compared across ranks)."""
+    import torch
+    import torch.distributed as dist
+    from comfyui_parallelanything_b200.exec.flux_exec import FluxExecutor
+    from comfyui_parallelanything_b200.exec.pack_cache import packed_table
+    from comfyui_parallelanything_b200.models import flux
+    from comfyui_parallelanything_b200.parallel import replicate_nvl
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=1024,
+                        mlp_ratio=4.0, num_heads=8, depth=2, depth_single_blocks=3)
+    res = {}
+    for method, fp8 in (("nvls", False), ("nvls", True), ("nccl", False)):
+        torch.manual_seed(100 + rank)
+        ex = FluxExecutor(flux.Flux(p).to(device=dev, dtype=torch.bfloat16).eval(), dev, fp8=fp8)
+        rep = replicate_nvl.broadcast_executor(ex, src=0, method=method, slot_bytes=8 << 20)   # small slots: many hand-offs
+        sums = []
+        for k, v in sorted(packed_table(ex).items()):
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                b = v.reshape(-1).view(torch.uint8)
+                sums.append(b.double().sum() + 3.0 * b[:64].double().sum() + 7.0 * b[-64:].double().sum())
+        mine = torch.stack(sums)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        same = all(bool(torch.equal(a, allv[0])) for a in allv)
+        res[f"{method}{'_fp8' if fp8 else ''}"] = dict(identical=same, tensors=len(sums), **rep)
+        del ex
+    if rank == 0:
+        ok = all(v["identical"] for v in res.values())
+        print("PA_SPMD " + json.dumps(dict(family="bcast", world=world, ok=ok, results=res)), flush=True)
     dist.destroy_process_group()
     return 0
 
