@@ -130,13 +130,14 @@ def replicate_inprocess(src_executor, dst_executors: Sequence[Any], method: str 
     devs = [src_dev] + [d.device for d in dst_executors]
     total = sum(_nbytes(s) for s, _ in pairs)
     why = ""
+    timing: Dict[str, float] = {}
     t0 = time.perf_counter()
     use = method
     if method in ("auto", "nvls"):
         try:
             if not all(C.multicast_supported(d.index) for d in devs):
                 raise RuntimeError("CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED is 0 on a device of the chain")
-            _nvls_inprocess(C, pairs, devs, slot_bytes)
+            timing = _nvls_inprocess(C, pairs, devs, slot_bytes)
             use = "nvls"
         except Exception as e:                        # fabric without multicast, or the driver refused the object
             if method == "nvls":
@@ -152,6 +153,10 @@ def replicate_inprocess(src_executor, dst_executors: Sequence[Any], method: str 
     dt = time.perf_counter() - t0
     rep = {"method": use, "bytes": total, "seconds": round(dt, 4), "gbps": round(total / max(dt, 1e-9) / 1e9, 1),
            "receivers": len(dst_executors)}
+    if timing:                                        # multicast object creation / binding vs the stores themselves
+        rep["team_setup_s"] = round(timing["setup"], 4)
+        rep["transfer_s"] = round(timing["transfer"], 4)
+        rep["transfer_gbps_per_receiver"] = round(total / max(timing["transfer"], 1e-9) / 1e9, 1)
     if why:
         rep["why_not_nvls"] = why
     return rep
@@ -178,13 +183,17 @@ def _chunks(pairs, slot_bytes: int):
         yield cur
 
 
-def _nvls_inprocess(C, pairs, devs, slot_bytes: int) -> None:
+def _nvls_inprocess(C, pairs, devs, slot_bytes: int) -> Dict[str, float]:
     bad = [s for s, _ in pairs if not s.is_contiguous() or s.data_ptr() % 16]
     if bad:
         raise RuntimeError("packed tensors must be contiguous and 16-byte aligned")
+    t0 = time.perf_counter()
     team = C.MulticastTeam([d.index for d in devs], 2 * slot_bytes, 0, False)
     try:
         team.bind_all()
+        for d in devs:
+            torch.cuda.synchronize(d)
+        t1 = time.perf_counter()
         slot = team.size() // 2
         slot -= slot % 256
         lead = devs[0]
@@ -217,6 +226,7 @@ def _nvls_inprocess(C, pairs, devs, slot_bytes: int) -> None:
             k += 1
         for d in devs:
             torch.cuda.synchronize(d)
+        return {"setup": t1 - t0, "transfer": time.perf_counter() - t1}
     finally:
         team.close()
 
@@ -276,7 +286,7 @@ def broadcast_executor(executor, src: int = 0, method: str = "nvls", slot_bytes:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 1:
             try:
-                _nvls_spmd(C, executor, src, rank, world, dev, slot_bytes)
+                rep.update(_nvls_spmd(C, executor, src, rank, world, dev, slot_bytes))
                 done = True
                 rep["method"] = "nvls"
             except Exception as e:                       # noqa: BLE001 - reported, then the NCCL path runs on all ranks
@@ -298,8 +308,9 @@ def broadcast_executor(executor, src: int = 0, method: str = "nvls", slot_bytes:
     return rep
 
 
-def _nvls_spmd(C, executor, src: int, rank: int, world: int, dev, slot_bytes: int) -> None:
+def _nvls_spmd(C, executor, src: int, rank: int, world: int, dev, slot_bytes: int) -> Dict[str, float]:
     import torch.distributed as dist
+    t0 = time.perf_counter()
     path = f"/tmp/pa_mc_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}.sock"
     if rank == src:
         team = C.MulticastTeam([dev.index], 2 * slot_bytes, world, True)
@@ -320,6 +331,8 @@ def _nvls_spmd(C, executor, src: int, rank: int, world: int, dev, slot_bytes: in
         dist.barrier()                                    # every device added ...
         team.bind_all()                                   # ... before anyone binds
         dist.barrier()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
         pairs = [(v, [v]) for v in packed_table(executor).values() if isinstance(v, torch.Tensor) and v.is_cuda]
         slot = team.size() // 2
         slot -= slot % 256
@@ -343,5 +356,9 @@ def _nvls_spmd(C, executor, src: int, rank: int, world: int, dev, slot_bytes: in
             k += 1
         dist.all_reduce(tick)
         torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        nb = sum(_nbytes(t) for t, _ in pairs)
+        return {"team_setup_s": round(t1 - t0, 4), "transfer_s": round(t2 - t1, 4),
+                "transfer_gbps_per_receiver": round(nb / max(t2 - t1, 1e-9) / 1e9, 1), "chunks": k}
     finally:
         team.close()

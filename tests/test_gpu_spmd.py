@@ -38,3 +38,17 @@ def test_spmd_weight_broadcast_nvls_or_nccl():
     res = json.loads(lines[-1][len("PA_SPMD "):])
     assert res["ok"] and res["world"] == n, res
     print("weight broadcast:", {k: (v["method"], v.get("gbps"), v.get("why_not_nvls")) for k, v in res["results"].items()})
+
+
+def test_flag_protocol_randomised_delay_stress():
+    """SURVEY §4.5: the release/acquire flag protocol under randomised producer/consumer skew (20 000 epochs here;
+    the 100 000-epoch run is committed under profiles/)."""
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29539", os.path.join(ROOT, "tools", "flag_stress.py"),
+           "--epochs", "20000"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("PA_FLAGS ")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1][len("PA_FLAGS "):])
+    assert res["ok"] and res["world"] == n and res["epochs"] == 20000, res
