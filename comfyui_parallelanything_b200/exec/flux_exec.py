@@ -130,6 +130,9 @@ class FluxExecutor(nn.Module):
         self._graphs = GraphCache(self.device, enabled=cuda_graphs)
         # fork the txt / img chains of the double blocks onto two streams with disjoint SM budgets (PA_DUAL_STREAM=0: off)
         self.dual_stream = os.environ.get("PA_DUAL_STREAM", "1") != "0"
+        # fp8: attention / GELU epilogues emit the next GEMM's MXFP8 A operand themselves (PA_FP8_FUSED_QUANT=0: separate
+        # quantise kernels in front of every GEMM)
+        self.fused_quant = os.environ.get("PA_FP8_FUSED_QUANT", "1") != "0"
         self._side = self._ev_fork = self._ev_join = None
         self.launches_per_step = 0
 
@@ -166,6 +169,17 @@ class FluxExecutor(nn.Module):
         ws["SVEC"] = e(B, hid)
         ws["MOD"] = e(B, self.mod_total)
         ws["OUT"] = e(B, self.params.out_channels // 4, H, Wd)
+        if self.fp8 and self.fused_quant:
+            # MXFP8 operands written directly by the producing epilogues (attention, GELU): e4m3 bytes + UE8M0 scale
+            # chunks (zero-initialised once: scale bytes of rows beyond the sequence are never written)
+            u8 = lambda *s: torch.zeros(*s, dtype=torch.uint8, device=d)  # noqa: E731
+            sfb = lambda rows, k: u8(B * ((rows + 127) // 128) * (k // 128) * 512)  # noqa: E731
+            ws["CAT8"], ws["CAT8_SF"] = u8(B, L, hid + mlp), sfb(L, hid + mlp)
+            ws["MH8I"], ws["MH8I_SF"] = u8(B, Li, mlp), sfb(Li, mlp)
+            ws["MH8T"], ws["MH8T_SF"] = u8(B, Lt, mlp), sfb(Lt, mlp)
+            ws["XM8"], ws["XM8_SF"] = u8(B, L, hid), sfb(L, hid)            # LayerNorm+modulate outputs, per chain
+            ws["XM8I"], ws["XM8I_SF"] = u8(B, Li, hid), sfb(Li, hid)
+            ws["XM8T"], ws["XM8T_SF"] = u8(B, Lt, hid), sfb(Lt, hid)
         m = flux_model.Flux.__new__(flux_model.Flux)
         m.patch_size = 2
         ids = flux_model.Flux.make_ids(m, 1, H, Wd, Lt, d)
@@ -175,14 +189,17 @@ class FluxExecutor(nn.Module):
         return ws
 
     # ------------------------------------------------------------------ schedule
-    def _lin(self, a, name: str, mode: str, **kw) -> int:
-        """One block Linear: bf16 tcgen05 GEMM, or (fp8) quantise the activation + block-scaled fp8 GEMM.
-        Returns the number of kernel launches."""
+    def _lin(self, a, name: str, mode: str, a8=None, **kw) -> int:
+        """One block Linear: bf16 tcgen05 GEMM, or (fp8) quantise the activation + block-scaled fp8 GEMM.  ``a8`` =
+        (e4m3 bytes, scale chunks) when the producer already emitted the MXFP8 operand.  Returns the launch count."""
         W = self.W
         if name + ".q" in W:
-            aq, sfa = ops.quantize_mxfp8(a)
-            ops.gemm_fp8(aq, sfa, W[name + ".q"], W[name + ".sf"], mode, W[name + ".tile"], bias=W[name + ".b"], **kw)
-            return 3
+            n = 1
+            if a8 is None:
+                a8 = ops.quantize_mxfp8(a)
+                n = 3
+            ops.gemm_fp8(a8[0], a8[1], W[name + ".q"], W[name + ".sf"], mode, W[name + ".tile"], bias=W[name + ".b"], **kw)
+            return n
         ops.gemm(a, W[name + ".w"], mode, bias=W[name + ".b"], **kw)
         return 1
 
@@ -244,8 +261,21 @@ class FluxExecutor(nn.Module):
                 self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
             side = self._side
 
+        fused8 = self.fp8 and self.fused_quant and hid % 256 == 0
+
+        def ln8(xs, s, sc, sh):
+            """LayerNorm + modulate straight to the MXFP8 A operand of the following GEMM."""
+            a8 = (ws["XM8I"], ws["XM8I_SF"]) if s == "img" else ((ws["XM8T"], ws["XM8T_SF"]) if s == "txt"
+                                                                  else (ws["XM8"], ws["XM8_SF"]))
+            C.layernorm_modulate_fp8(xs, a8[0], a8[1], sc, sh, 1e-6)
+            return a8
+
         def pre(i, s, xs, xms, seq_off):
             k = ("d", i, s)
+            if fused8 and f"d{i}.{s}.qkv.q" in W:
+                a8 = ln8(xs, s, self._mod(ws, k, 1), self._mod(ws, k, 0))
+                return 1 + self._lin(None, f"d{i}.{s}.qkv", "qkv_rope", a8=a8, q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
+                                     k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
             ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
             return 1 + self._lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
                                  k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
@@ -253,6 +283,12 @@ class FluxExecutor(nn.Module):
         def post(i, s, xs, xms, a, mh):
             k = ("d", i, s)
             m = self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
+            if fused8 and f"d{i}.{s}.mlp0.q" in W and f"d{i}.{s}.mlp2.q" in W:
+                a8 = ln8(xs, s, self._mod(ws, k, 4), self._mod(ws, k, 3))
+                m8 = (ws["MH8I"], ws["MH8I_SF"]) if s == "img" else (ws["MH8T"], ws["MH8T_SF"])
+                m += self._lin(None, f"d{i}.{s}.mlp0", "gelu", a8=a8, out8=m8[0], sf8=m8[1])   # GELU + MX quantisation
+                m += self._lin(None, f"d{i}.{s}.mlp2", "gate_res", a8=m8, out=xs, residual=xs, gate=self._mod(ws, k, 5))
+                return m + 1
             ops.layernorm_modulate(xs, xms, scale=self._mod(ws, k, 4), shift=self._mod(ws, k, 3))
             m += self._lin(xms, f"d{i}.{s}.mlp0", "gelu", out=mh)
             m += self._lin(mh, f"d{i}.{s}.mlp2", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 5))
@@ -286,6 +322,16 @@ class FluxExecutor(nn.Module):
         # ---- single-stream blocks
         for i in range(self.n_single):
             k = ("s", i)
+            if fused8 and f"s{i}.l1.q" in W and f"s{i}.l2.q" in W:
+                # linear2's A operand [attention | GELU(mlp)] is written as MXFP8 by its two producers
+                c8 = (ws["CAT8"], ws["CAT8_SF"])
+                a8 = ln8(X, "all", self._mod(ws, k, 1), self._mod(ws, k, 0))
+                n += self._lin(None, f"s{i}.l1", "qkv_rope", a8=a8, q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"],
+                               k_scale=W[f"s{i}.ks"], rope=ROPE, seq_off=0, out8=c8[0], sf8=c8[1], out8_col_off=hid)
+                C.attention_fp8out(Q, K, V, c8[0], c8[1], 128 ** -0.5)
+                n += self._lin(None, f"s{i}.l2", "gate_res", a8=c8, out=X, residual=X, gate=self._mod(ws, k, 2))
+                n += 2
+                continue
             ops.layernorm_modulate(X, XM, scale=self._mod(ws, k, 1), shift=self._mod(ws, k, 0))
             n += self._lin(XM, f"s{i}.l1", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"], k_scale=W[f"s{i}.ks"],
                            rope=ROPE, seq_off=0, out=CAT, mlp_col_off=hid)

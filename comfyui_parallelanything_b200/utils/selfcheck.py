@@ -983,3 +983,53 @@ def lookalike_models_get_native_executors():
     r["unet_mean_rel"] = r2["mean_rel"]
     r["ok"] = r["ok"] and r2["ok"]
     return r
+
+
+@check
+def mxfp8_fused_quant_epilogues():
+    """Producers that emit the NEXT GEMM's MXFP8 A operand themselves: GELU epilogue (224-wide tiles), the GELU'd MLP
+    half of the single-block linear1 (drain-first QKV epilogue) and the attention epilogue.  The dequantised result
+    must match the fp32 reference to e4m3 precision, and agree with quantising the bf16 output separately."""
+    import torch.nn.functional as F
+    C_ = ops.require()
+    dev = _dev()
+    B, rows, K, N = 2, 200, 512, 896
+    a, w, bias = _rand(B, rows, K), _rand(N, K, scale=0.06), _rand(N)
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, wsf = ops.quantize_mxfp8(w, 224)
+    out8 = torch.zeros(B, rows, N, dtype=torch.uint8, device=dev)
+    sf8 = torch.zeros(B * ((rows + 127) // 128) * (N // 128) * 512, dtype=torch.uint8, device=dev)
+    ops.gemm_fp8(aq, sfa, wq, wsf, "gelu", 224, bias=bias, out8=out8, sf8=sf8)
+    ref = F.gelu(ops.dequantize_mxfp8(aq, sfa) @ ops.dequantize_mxfp8(wq, wsf, 224)[0].t() + bias.float(), approximate="tanh")
+    r = _cmp("gelu_fp8out", ops.dequantize_mxfp8(out8, sf8), ref, 0.06, hard=16.0)
+    # single-block linear1: 2 heads of qkv + 256 MLP columns, fp8 MLP half lands at column offset 256 of a [B, L, 512] buffer
+    H, L = 2, 256
+    hid = H * 128
+    a1, w1 = _rand(B, L, hid), _rand(3 * hid + 256, hid, scale=0.08)
+    b1 = _rand(3 * hid + 256)
+    aq1, sfa1 = ops.quantize_mxfp8(a1)
+    wq1, wsf1 = ops.quantize_mxfp8(w1, 256)
+    q, k, v = (torch.zeros(B, H, L, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    qs, ks = _rand(128) + 1.0, _rand(128) + 1.0
+    cat8 = torch.zeros(B, L, hid + 256, dtype=torch.uint8, device=dev)
+    cat8_sf = torch.zeros(B * (L // 128) * ((hid + 256) // 128) * 512, dtype=torch.uint8, device=dev)
+    ops.gemm_fp8(aq1, sfa1, wq1, wsf1, "qkv_rope", 256, bias=b1, q=q, k=k, v=v, q_scale=qs, k_scale=ks,
+                 rope=_rope_table(L, dev)[1], seq_off=0, out8=cat8, sf8=cat8_sf, out8_col_off=hid)
+    y = ops.dequantize_mxfp8(aq1, sfa1) @ ops.dequantize_mxfp8(wq1, wsf1, 256)[0].t() + b1.float()
+    r2 = _cmp("l1_mlp_fp8out", ops.dequantize_mxfp8(cat8, cat8_sf)[:, :, hid:], F.gelu(y[:, :, 3 * hid:], approximate="tanh"),
+              0.06, hard=16.0)
+    # attention with MX-quantised output into columns [0, hid) of the same buffer
+    C_.attention_fp8out(q, k, v, cat8, cat8_sf, 128 ** -0.5)
+    want = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).permute(0, 2, 1, 3).reshape(B, L, hid)
+    r3 = _cmp("attention_fp8out", ops.dequantize_mxfp8(cat8, cat8_sf)[:, :, :hid], want, 0.06, hard=16.0)
+    # LayerNorm + modulate with MXFP8 output
+    xl, sc, sh = _rand(B, 300, 768), _rand(B, 768, scale=0.3), _rand(B, 768, scale=0.3)
+    q8 = torch.zeros(B, 300, 768, dtype=torch.uint8, device=dev)
+    s8 = torch.zeros(B * 3 * 6 * 512, dtype=torch.uint8, device=dev)
+    C_.layernorm_modulate_fp8(xl, q8, s8, sc, sh, 1e-6)
+    lw = F.layer_norm(xl.float(), (768,), eps=1e-6) * (1 + sc.float()[:, None]) + sh.float()[:, None]
+    r4 = _cmp("ln_mod_fp8out", ops.dequantize_mxfp8(q8, s8), lw, 0.06, hard=16.0)
+    r["l1_mlp_mean_rel"], r["attention_mean_rel"], r["ln_mean_rel"] = r2["mean_rel"], r3["mean_rel"], r4["mean_rel"]
+    r["ok"] = r["ok"] and r2["ok"] and r3["ok"] and r4["ok"] and max(r["mean_rel"], r2["mean_rel"], r3["mean_rel"],
+                                                                   r4["mean_rel"]) < 0.035
+    return r

@@ -60,6 +60,23 @@ static void parse_epilogue(const py::kwargs& kw, pa::GemmParams& p, bool check_s
     p.gate = reinterpret_cast<const __nv_bfloat16*>(g.data_ptr());
     p.gate_bstride = g.dim() >= 2 ? g.stride(0) : 0;
   }
+  if (has(kw, "out8")) {
+    // fused MXFP8 output: e4m3 bytes [batch, rows8, ld8] contiguous + scale chunks; written at column out8_col_off
+    Tensor o8 = ten(kw, "out8");
+    Tensor s8 = ten(kw, "sf8");
+    TORCH_CHECK(o8.element_size() == 1 && s8.element_size() == 1 && o8.is_contiguous() && s8.is_contiguous() &&
+                    o8.dim() == 3, "out8 must be contiguous uint8 [batch, rows, K], sf8 contiguous uint8");
+    TORCH_CHECK(o8.size(0) == p.batch && o8.size(1) >= p.rows && o8.size(2) % 128 == 0, "out8 shape mismatch");
+    p.out8 = reinterpret_cast<uint8_t*>(o8.data_ptr());
+    p.sf8 = reinterpret_cast<uint8_t*>(s8.data_ptr());
+    p.ld8 = o8.size(2);
+    p.out8_bstride = o8.size(1) * o8.size(2);
+    p.sf8_mtiles = (int)((o8.size(1) + 127) / 128);
+    p.sf8_kchunks = (int)(o8.size(2) / 128);
+    p.out8_col_off = has(kw, "out8_col_off") ? kw["out8_col_off"].cast<long long>() : 0;
+    TORCH_CHECK(p.out8_col_off % 32 == 0, "out8_col_off must be a multiple of 32");
+    TORCH_CHECK(s8.numel() >= (int64_t)p.batch * p.sf8_mtiles * p.sf8_kchunks * 512, "sf8 too small");
+  }
 }
 
 // gemm(A, W, mode, out=..., bias=..., residual=..., gate=..., q=,k=,v=,q_scale=,k_scale=,rope=,heads=,seq_off=,
@@ -143,7 +160,7 @@ static void parse_modes(int mode, const py::kwargs& kw, pa::GemmParams& p) {
     }
     p.mlp_cols = p.N - 3 * p.heads * 128;
     p.mlp_col_off = has(kw, "mlp_col_off") ? kw["mlp_col_off"].cast<long long>() : 0;
-    TORCH_CHECK(p.mlp_cols == 0 || p.out != nullptr, "single-block QKV+MLP needs out=");
+    TORCH_CHECK(p.mlp_cols == 0 || p.out != nullptr || p.out8 != nullptr, "single-block QKV+MLP needs out= or out8=");
   }
   if (mode == pa::EPI_EULER_UNPATCH) {
     p.C = kw["C"].cast<int>();
@@ -162,7 +179,7 @@ static void parse_modes(int mode, const py::kwargs& kw, pa::GemmParams& p) {
       TORCH_CHECK(p.x_in != nullptr, "Euler update needs x_in");
     }
   } else {
-    TORCH_CHECK(p.out != nullptr || mode == pa::EPI_QKV_ROPE, "gemm: out= required");
+    TORCH_CHECK(p.out != nullptr || p.out8 != nullptr || mode == pa::EPI_QKV_ROPE, "gemm: out= (or out8=) required");
   }
 }
 
@@ -201,6 +218,23 @@ static void layernorm_modulate(Tensor x, Tensor out, c10::optional<Tensor> scale
                                gamma ? gamma->data_ptr() : nullptr, beta ? beta->data_ptr() : nullptr, b, rows,
                                (int)x.size(-1), (float)eps, cur_stream()),
         "layernorm_modulate");
+}
+
+// LayerNorm + (1 + scale) * . + shift with MXFP8 output: q8 uint8 [B, rows, D] contiguous, sf8 scale chunks
+static void layernorm_modulate_fp8(Tensor x, Tensor q8, Tensor sf8, Tensor scale, Tensor shift, double eps) {
+  c10::cuda::CUDAGuard guard(x.device());
+  int b, rows;
+  long long ldx, xbs;
+  view3(x, b, rows, ldx, xbs);
+  const int D = (int)x.size(-1);
+  TORCH_CHECK(q8.is_contiguous() && q8.element_size() == 1 && q8.numel() == (int64_t)b * rows * D, "q8 must be [B, rows, D] uint8");
+  TORCH_CHECK(sf8.is_contiguous() && sf8.numel() >= (int64_t)b * ((rows + 127) / 128) * (D / 128) * 512, "sf8 too small");
+  TORCH_CHECK(scale.stride(-1) == 1 && shift.stride(-1) == 1);
+  const long long mod_bs = scale.dim() >= 2 ? scale.stride(0) : 0;
+  TORCH_CHECK((shift.dim() >= 2 ? shift.stride(0) : 0) == mod_bs, "scale/shift batch strides differ");
+  check(pa::layernorm_modulate_fp8(x.data_ptr(), ldx, xbs, q8.data_ptr(), sf8.data_ptr(), scale.data_ptr(),
+                                   shift.data_ptr(), mod_bs, b, rows, D, (float)eps, cur_stream()),
+        "layernorm_modulate_fp8");
 }
 
 // out = [residual +] [tanh](gate) * rms(x) * weight * (1 + scale); scale / gate: [B, D] views (or [D]), any may be None
@@ -402,6 +436,23 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
         "attention");
 }
 
+// attention with MX-quantised output: out8 uint8 [B, rows8 >= Lq, ld8 >= H*128] contiguous (e4m3), sf8 scale chunks
+static void attention_fp8out(Tensor q, Tensor k, Tensor v, Tensor out8, Tensor sf8, double scale) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && q.size(3) == 128 && k.size(3) == 128 && v.size(3) == 128, "head_dim 128 required");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && q.scalar_type() == at::kBFloat16);
+  TORCH_CHECK(out8.dim() == 3 && out8.is_contiguous() && out8.element_size() == 1 && sf8.is_contiguous() &&
+                  out8.size(0) == q.size(0) && out8.size(1) >= q.size(2), "out8 must be uint8 [B, rows, K] contiguous");
+  TORCH_CHECK(sf8.numel() >= out8.size(0) * ((out8.size(1) + 127) / 128) * (out8.size(2) / 128) * 512, "sf8 too small");
+  long long qs[3] = {q.stride(0), q.stride(1), q.stride(2)};
+  long long ks[3] = {k.stride(0), k.stride(1), k.stride(2)};
+  long long vs[3] = {v.stride(0), v.stride(1), v.stride(2)};
+  check(pa::attention2_fp8out(q.data_ptr(), k.data_ptr(), v.data_ptr(), out8.data_ptr(), sf8.data_ptr(), out8.size(2),
+                              out8.size(1), (int)q.size(0), (int)q.size(1), (int)q.size(2), (int)k.size(2), qs, ks, vs,
+                              (float)scale, cur_stream()),
+        "attention_fp8out");
+}
+
 static Tensor attention3_trace() {
   Tensor t = at::zeros({7, 64, 8}, at::TensorOptions().dtype(at::kLong));
   check(pa::attention3_trace_read(reinterpret_cast<long long*>(t.data_ptr<int64_t>())), "attention3_trace_read");
@@ -457,6 +508,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("w_tile"));
   m.def("quantize_mxfp8", &quantize_mxfp8, py::arg("x"), py::arg("tile_rows") = 128);
   m.def("conv", &conv, py::arg("x"), py::arg("w"), py::arg("taps"), py::arg("stride"), py::arg("mode"));
+  m.def("layernorm_modulate_fp8", &layernorm_modulate_fp8);
   m.def("layernorm_modulate", &layernorm_modulate, py::arg("x"), py::arg("out"), py::arg("scale") = py::none(),
         py::arg("shift") = py::none(), py::arg("gamma") = py::none(), py::arg("beta") = py::none(),
         py::arg("eps") = 1e-6);
@@ -476,6 +528,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("attention", &attention, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("scale"),
         py::arg("variant") = 1);
   m.def("attention2_trace", &attention2_trace);
+  m.def("attention_fp8out", &attention_fp8out);
   m.def("attention3_trace", &attention3_trace);
   m.def("copy_rows", &copy_rows);
   m.def("rmsnorm_mod", &rmsnorm_mod, py::arg("x"), py::arg("out"), py::arg("weight") = py::none(),

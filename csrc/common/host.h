@@ -34,6 +34,8 @@ int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, G
 int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,
                 const void* weight, const void* scale, const void* gate, long long mod_bs, const void* residual,
                 long long ldr, long long r_bs, int batch, int rows, int D, float eps, int tanh_gate, cudaStream_t st);
+int layernorm_modulate_fp8(const void* x, long long ldx, long long x_bs, void* q8, void* sf8, const void* scale,
+                           const void* shift, long long mod_bs, int batch, int rows, int D, float eps, cudaStream_t st);
 int layernorm_modulate(const void* x, long long ldx, long long x_bstride, void* out, long long ldo,
                        long long o_bstride, const void* scale, const void* shift, long long mod_bstride,
                        const void* gamma, const void* beta, int batch, int rows, int D, float eps, cudaStream_t st);
@@ -79,6 +81,9 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
                     int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
                     const long long* v_strides, float scale, cudaStream_t st);
 
+int attention2_fp8out(const void* q, const void* k, const void* v, void* out8, void* sf8, long long ld8, long long rows8,
+                      int B, int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs,
+                      float scale, cudaStream_t st);
 int attention2_debug(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                      int H, int Lq, int Lk, int dbg, const long long* q_strides, const long long* k_strides,
                      const long long* v_strides, float scale, cudaStream_t st);

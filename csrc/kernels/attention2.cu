@@ -10,6 +10,7 @@
 //               columns of S_X once S_X sits in registers and feeds the P.V MMA as a TMEM A operand.
 //   registers   setmaxnreg: 56 for the producer/MMA warpgroup, 208 for the softmax warpgroups.
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include "../common/host.h"
@@ -32,6 +33,15 @@ __device__ long long g_trace[5 * 64 * 8];
 #ifndef PA_POLY_MASK
 #define PA_POLY_MASK 0x22
 #endif
+
+// Optional MXFP8 output (the next GEMM's A operand): e4m3 bytes [B, rows8, ld8] + UE8M0 scale chunks in the layout
+// of gemm_mxfp8.cu.  q == nullptr -> bf16 output as usual.
+struct Fp8Out {
+  uint8_t* q;
+  uint8_t* sf;
+  long long ld8, bstride;
+  int mtiles, kchunks;
+};
 
 template <int D>
 struct Cfg {
@@ -57,7 +67,7 @@ template <int D, int DBG, int NS>
 __global__ void __launch_bounds__(128 + 256 * NS, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out, long long ldo,
-                  long long o_bstride, int H, int Lq, int Lk, float scale_log2) {
+                  long long o_bstride, int H, int Lq, int Lk, float scale_log2, const Fp8Out f8) {
   using C = Cfg<D>;
   constexpr int BN = C::BN;
   constexpr uint32_t SLICE = C::SLICE, TILE = C::TILE;
@@ -379,6 +389,49 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const float inv = 1.0f / l;
     const int b = bh / H, h = bh - b * H;
     __nv_bfloat16* dst = out + b * o_bstride + static_cast<long long>(q_row) * ldo + h * D + half * OW;
+    if (f8.q != nullptr && NS == 1 && D == 128) {
+      // MX-quantised output: each 32-column TMEM chunk of this thread's row is one MX block (amax -> UE8M0 scale ->
+      // e4m3); half the bytes of the bf16 store and no separate quantise kernel before the projection GEMM
+      uint8_t* qrow = f8.q + b * f8.bstride + static_cast<long long>(q_row) * f8.ld8 + h * D;
+      uint32_t sfw = 0;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t t[32];
+        ptx::tmem_ld_32x32b_x32(o_addr + c * 32, t);
+        ptx::tmem_ld_wait();
+        float amax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          t[i] = __float_as_uint(__uint_as_float(t[i]) * inv);
+          amax = fmaxf(amax, fabsf(__uint_as_float(t[i])));
+        }
+        int e = -127;
+        if (amax > 0.f) {
+          e = static_cast<int>(ceilf(log2f(amax * (1.0f / 448.0f))));
+          e = max(-127, min(127, e));
+        }
+        const float sc = exp2f(static_cast<float>(-e));
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(
+              make_float2(__uint_as_float(t[4 * j]) * sc, __uint_as_float(t[4 * j + 1]) * sc), __NV_SATFINITE, __NV_E4M3);
+          const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(
+              make_float2(__uint_as_float(t[4 * j + 2]) * sc, __uint_as_float(t[4 * j + 3]) * sc), __NV_SATFINITE, __NV_E4M3);
+          pk[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+        }
+        if (q_row < Lq) {
+          uint4* d = reinterpret_cast<uint4*>(qrow + c * 32);
+          d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        sfw |= static_cast<uint32_t>(e + 127) << (8 * c);
+      }
+      if (q_row < Lq) {
+        const long long chunk = (static_cast<long long>(b) * f8.mtiles + (q_row >> 7)) * f8.kchunks + h;   // D == 128
+        *reinterpret_cast<uint32_t*>(f8.sf + chunk * 512 + (q_row & 31) * 16 + ((q_row >> 5) & 3) * 4) = sfw;
+      }
+    } else
 #pragma unroll 1
     for (int c = 0; c < OW / 32; ++c) {
       uint32_t t[32];
@@ -413,7 +466,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 template <int D, int DBG, int NS = 1>
 static int launch(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
                   int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs, float scale,
-                  cudaStream_t st) {
+                  cudaStream_t st, Fp8Out f8 = Fp8Out{nullptr, nullptr, 0, 0, 0, 0}) {
   using C = Cfg<D>;
   CUtensorMap tq, tk, tv;
   const uint32_t box[4] = {64, 128, 1, 1};
@@ -436,7 +489,7 @@ static int launch(const void* q, const void* k, const void* v, void* out, long l
   }
   dim3 grid((Lq + 255) / 256, B * H);
   attention2_kernel<D, DBG, NS><<<grid, 128 + 256 * NS, C::SMEM, st>>>(tq, tk, tv, static_cast<__nv_bfloat16*>(out), ldo, o_bstride, H, Lq,
-                                                   Lk, scale * 1.4426950408889634f);
+                                                   Lk, scale * 1.4426950408889634f, f8);
   return (int)cudaGetLastError();
 }
 }  // namespace a2
@@ -449,6 +502,18 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
   if (D == 128) return a2::launch<128, 0>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
   if (D == 64) return a2::launch<64, 0>(q, k, v, out, ldo, o_bstride, B, H, Lq, Lk, qs, ks, vs, scale, st);
   return -11;
+}
+
+// head_dim 128 only: the output goes out MX-quantised (e4m3 [B, rows8, ld8] + scale chunks) for a following fp8 GEMM
+int attention2_fp8out(const void* q, const void* k, const void* v, void* out8, void* sf8, long long ld8, long long rows8,
+                      int B, int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs,
+                      float scale, cudaStream_t st) {
+  for (int i = 0; i < 3; ++i)
+    if (qs[i] % 8 || ks[i] % 8 || vs[i] % 8) return -10;
+  if (ld8 % 128 || H * 128 > ld8) return -12;
+  a2::Fp8Out f8{static_cast<uint8_t*>(out8), static_cast<uint8_t*>(sf8), ld8, rows8 * ld8,
+                static_cast<int>((rows8 + 127) / 128), static_cast<int>(ld8 / 128)};
+  return a2::launch<128, 0>(q, k, v, nullptr, 0, 0, B, H, Lq, Lk, qs, ks, vs, scale, st, f8);
 }
 
 // timing experiments (D = 128 only): dbg = DBG mask (see attention2_kernel) + 128 for one softmax warpgroup per tile

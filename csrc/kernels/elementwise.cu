@@ -2,6 +2,7 @@
 // LayerNorm + AdaLN modulate, sinusoidal timestep embedding, patchify (NCHW latent -> tokens, source may be a
 // peer GPU), SiLU/add, GroupNorm(+SiLU) NHWC, CFG + Euler update with (peer) store, cross-GPU flag words.
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include "../common/host.h"
@@ -120,14 +121,17 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const __nv_bfloat16* __rest
 // 2 scale, 3 shift), so no predicated-off instructions are issued, and the affine part is folded into ONE fma per
 // element:  y = x * m + c  with  m = rstd * gamma * (1 + scale),  c = (-mean * rstd * gamma + beta) * (1 + scale) + shift.
 // The generic kernel above issued ~25 instructions per element (ncu: 43 % issue-slot utilisation, 2.2 TB/s); this is ~10.
-template <int MAX_VEC, int FLAGS>
+// F8: the output is the next GEMM's MXFP8 A operand (e4m3 [batch, rows, D] contiguous + UE8M0 scale chunks in the
+// gemm_mxfp8.cu layout) instead of bf16: four neighbouring lanes hold one 32-element MX block (8 elements each), its
+// amax is two shuffles away; `out` then points at the e4m3 bytes and `sf8` at the scale chunks.
+template <int MAX_VEC, int FLAGS, bool F8 = false>
 __global__ void __launch_bounds__(256) ln_mod_fast_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                                                           long long x_bs, __nv_bfloat16* __restrict__ out, long long ldo,
                                                           long long o_bs, const __nv_bfloat16* __restrict__ scale,
                                                           const __nv_bfloat16* __restrict__ shift, long long mod_bs,
                                                           const __nv_bfloat16* __restrict__ gamma,
                                                           const __nv_bfloat16* __restrict__ beta, int batch, int rows,
-                                                          int D, float eps) {
+                                                          int D, float eps, uint8_t* __restrict__ sf8 = nullptr) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= batch * rows) return;
@@ -201,9 +205,64 @@ __global__ void __launch_bounds__(256) ln_mod_fast_kernel(const __nv_bfloat16* _
       unpack8(buf[i], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], m[e], c[e]);
-      orow[idx] = pack8(v);
+      if (F8) {
+        // D % 32 == 0 (checked on the host), so the four lanes of an MX block are all inside `idx < nvec` together
+        float amax = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(v[e]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        int ex = -127;
+        if (amax > 0.f) {
+          ex = static_cast<int>(ceilf(log2f(amax * (1.0f / 448.0f))));
+          ex = max(-127, min(127, ex));
+        }
+        const float inv = exp2f(static_cast<float>(-ex));
+        uint32_t pk[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const __nv_fp8x2_storage_t lo =
+              __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j] * inv, v[4 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+          const __nv_fp8x2_storage_t hi =
+              __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j + 2] * inv, v[4 * j + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+          pk[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+        }
+        uint8_t* q8 = reinterpret_cast<uint8_t*>(out) + (static_cast<long long>(b) * rows + r) * D;
+        *reinterpret_cast<uint2*>(q8 + idx * 8) = make_uint2(pk[0], pk[1]);
+        if ((lane & 3) == 0) {
+          const int kb = idx >> 2;                                          // 32-element block index inside the row
+          const long long chunk = (static_cast<long long>(b) * ((rows + 127) >> 7) + (r >> 7)) * (D >> 7) + (kb >> 2);
+          sf8[chunk * 512 + (r & 31) * 16 + ((r >> 5) & 3) * 4 + (kb & 3)] = static_cast<uint8_t>(ex + 127);
+        }
+      } else {
+        orow[idx] = pack8(v);
+      }
     }
   }
+}
+
+// LayerNorm + modulate with MXFP8 output (scale + shift present, the FLUX case): q8 [batch, rows, D] e4m3 contiguous,
+// sf8 scale chunks (zero-initialised by the caller).
+int layernorm_modulate_fp8(const void* x, long long ldx, long long x_bs, void* q8, void* sf8, const void* scale,
+                           const void* shift, long long mod_bs, int batch, int rows, int D, float eps, cudaStream_t st) {
+  if (D % 256 || ldx % 8 || x_bs % 8 || mod_bs % 8 || !scale || !shift) return -1;   // whole warps per vector step
+  const long long warps = static_cast<long long>(batch) * rows;
+  const int threads = 256;
+  const int blocks = static_cast<int>((warps * 32 + threads - 1) / threads);
+  auto X = static_cast<const __nv_bfloat16*>(x);
+  auto SC = static_cast<const __nv_bfloat16*>(scale);
+  auto SH = static_cast<const __nv_bfloat16*>(shift);
+  auto O = static_cast<__nv_bfloat16*>(q8);
+  auto S8 = static_cast<uint8_t*>(sf8);
+  if (D <= 32 * 8 * 4)
+    ln_mod_fast_kernel<4, 12, true><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, 0, 0, SC, SH, mod_bs, nullptr, nullptr, batch, rows, D, eps, S8);
+  else if (D <= 32 * 8 * 12)
+    ln_mod_fast_kernel<12, 12, true><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, 0, 0, SC, SH, mod_bs, nullptr, nullptr, batch, rows, D, eps, S8);
+  else if (D <= 32 * 8 * 20)
+    ln_mod_fast_kernel<20, 12, true><<<blocks, threads, 0, st>>>(X, ldx, x_bs, O, 0, 0, SC, SH, mod_bs, nullptr, nullptr, batch, rows, D, eps, S8);
+  else
+    return -2;
+  return (int)cudaGetLastError();
 }
 
 template <int FLAGS>

@@ -111,7 +111,12 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
   // Producer and MMA roles run as whole warps on warp-uniform values with one elected lane issuing (inside a
   // `lane == 0` branch ptxas wraps every UTMALDG / UTCQMMA in an ELECT + R2UR.BROADCAST waterfall loop).
-  if (warp_u == 0) {
+  // Single accumulator (ACC == 1): the epilogue warps keep a whole 128-column accumulator row in registers (drain-first
+  // epilogue below), so registers move from the producer / MMA warpgroup to the two epilogue warpgroups.  The
+  // setmaxnreg sits INSIDE each role's branch so that ptxas allocates the branch with that budget.
+  if (warp < 4) {
+   if constexpr (ACC == 1) ptx::setmaxnreg_dec<72>();   // 128*72 + 256*216 == 384*168: the pool is what WG0 frees
+   if (warp_u == 0) {
     const bool leader = ptx::elect_one();
     const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
     int stage = 0;
@@ -177,7 +182,9 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
+   }
+  } else {
+    if constexpr (ACC == 1) ptx::setmaxnreg_inc<216>();
     // eight epilogue warps, two per TMEM lane quadrant: the fp8 main loop is twice as fast as the bf16 one, so the
     // epilogue (same cost per element) would otherwise set the tile period (see gemm_2cta.cuh)
     constexpr int H0 = BN >= 256 ? 128 : (BN > 128 ? 128 : 64);      // columns of the first half: 128 | 128 | 64
@@ -195,6 +202,28 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::mbar_wait(&tfull[acc], ACC == 2 ? ((it >> 1) & 1) : (it & 1));
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
+      if constexpr (ACC == 1 && BN == 256) {
+        if (p.mode == EPI_QKV_ROPE) {
+          // drain-first: this warp's 32 rows x 128 columns (one attention head / 128 MLP columns) -> registers, hand
+          // the single accumulator back to the MMA warp, THEN do the RMSNorm / RoPE / GELU math and the stores while
+          // the next tile's main loop already runs (measured before: 1.53 PFLOP/s with the tensor pipe idle for the
+          // whole epilogue vs 2.5 PFLOP/s for the double-buffered 224-wide tiles).
+          const int ng = nt * BN + half * 128;
+          const bool live = ng < p.N;
+          uint32_t areg[128];
+          if (live) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              ptx::tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&areg[c * 32]));
+            ptx::tmem_ld_wait();
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+          if (live) epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          continue;
+        }
+      }
       if (half == 0)
         epilogue_tile<H0>(p, taddr, b, row, row < p.rows, nt * BN);
       else if (nt * BN + H0 < p.N)

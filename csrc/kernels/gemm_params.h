@@ -31,6 +31,14 @@ struct GemmParams {
   long long ldr, res_bstride;
   const __nv_bfloat16* gate;        // [batch, N] with stride gate_bstride
   long long gate_bstride;
+  // Fused MXFP8 output (the NEXT GEMM's A operand, written by this epilogue instead of bf16 + a quantise kernel):
+  // EPI_BIAS_GELU: every column; EPI_QKV_ROPE: the GELU'd MLP columns.  e4m3 bytes row-major [batch, rows8, ld8]
+  // plus UE8M0 scale chunks in the layout of gemm_mxfp8.cu (128-row x 128-column chunks of 512 bytes).
+  uint8_t* out8;                    // nullptr = bf16 output as usual
+  uint8_t* sf8;
+  long long ld8, out8_bstride;      // row length / batch stride in bytes
+  long long out8_col_off;           // destination column of the first fp8 column (multiple of 32)
+  int sf8_mtiles, sf8_kchunks;      // 128-row tiles per batch, ld8 / 128
   // QKV
   __nv_bfloat16 *q, *k, *v;         // [batch, H, seq_total, 128]
   const __nv_bfloat16 *q_scale, *k_scale;   // [128] RMSNorm weights

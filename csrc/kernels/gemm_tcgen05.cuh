@@ -14,6 +14,8 @@
 // + Euler update stored straight into the lead GPU's buffer over NVLink.
 #pragma once
 #include "../common/ptx.cuh"
+#include <cuda_fp8.h>
+
 #include "gemm_params.h"
 
 namespace pa {
@@ -89,6 +91,152 @@ __device__ __forceinline__ void acc8(const uint32_t (&r)[32], int g, const __nv_
     ldg8(bias_at, bv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) x[e] += bv[e];
+  }
+}
+
+// One MX block: 32 consecutive fp32 values of a row -> 32 e4m3 bytes at `dst` (32-byte aligned) and the UE8M0 scale
+// byte (returned).  Same arithmetic as quantize_mxfp8_kernel: scale = 2^ceil(log2(amax / 448)).
+__device__ __forceinline__ uint32_t mx_quant32_store(const float (&v)[32], uint8_t* dst, bool do_store) {
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
+  int e = -127;
+  if (amax > 0.f) {
+    e = static_cast<int>(ceilf(log2f(amax * (1.0f / 448.0f))));
+    e = max(-127, min(127, e));
+  }
+  const float inv = exp2f(static_cast<float>(-e));
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_fp8x2_storage_t lo =
+        __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j] * inv, v[4 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+    const __nv_fp8x2_storage_t hi =
+        __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j + 2] * inv, v[4 * j + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+    pk[j] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+  }
+  if (do_store) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    d[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  return static_cast<uint32_t>(e + 127);
+}
+
+// scale byte of (batch b, row, destination column dcol) inside the chunk layout
+__device__ __forceinline__ uint8_t* mx_sf_ptr(const GemmParams& p, int b, int row, long long dcol) {
+  const long long chunk = (static_cast<long long>(b) * p.sf8_mtiles + (row >> 7)) * p.sf8_kchunks + (dcol >> 7);
+  return p.sf8 + chunk * 512 + (row & 31) * 16 + ((row >> 5) & 3) * 4 + ((dcol >> 5) & 3);
+}
+
+// QKV + RoPE (+ GELU'd MLP columns) epilogue of ONE 128-column head group whose accumulator row already sits in
+// registers.  Used by single-accumulator mainloops (block-scaled fp8, 256-wide tiles): the epilogue warps first drain
+// their TMEM slice into registers and hand the accumulator back to the MMA warp, so the next tile's main loop runs
+// under this (expensive) math instead of waiting for it - double buffering through the register file.
+__device__ __forceinline__ void epilogue_qkv_from_regs(const GemmParams& p, const uint32_t (&acc)[128], int b, int row,
+                                                       bool row_ok, int ng) {
+  const int qkv_cols = 3 * p.heads * 128;
+  if (ng < qkv_cols) {
+    const int sec = ng / (p.heads * 128);
+    const int head = (ng - sec * p.heads * 128) >> 7;
+    float rrms = 1.0f;
+    if (sec < 2) {
+      float ss = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[g * 8 + e]);
+        if (p.bias) {
+          float bv[8];
+          ldg8(p.bias + ng + g * 8, bv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] += bv[e];
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += x[e] * x[e];
+      }
+      rrms = rsqrtf(ss * (1.0f / 128.0f) + p.qk_eps);
+    }
+    __nv_bfloat16* dst_base = (sec == 0 ? p.q : (sec == 1 ? p.k : p.v));
+    const long long pos = p.seq_off + row;
+    __nv_bfloat16* dst = dst_base + ((static_cast<long long>(b) * p.heads + head) * p.seq_total + pos) * 128;
+    const __nv_bfloat16* nw = sec == 0 ? p.q_scale : p.k_scale;
+    const bool do_rope = sec < 2 && p.rope != nullptr && row_ok;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[g * 8 + e]);
+      if (p.bias) {
+        float bv[8];
+        ldg8(p.bias + ng + g * 8, bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] += bv[e];
+      }
+      if (sec < 2) {
+        float w[8];
+        ldg8(nw + g * 8, w);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = x[e] * rrms * w[e];
+        if (do_rope) {
+          const float4* rp = reinterpret_cast<const float4*>(p.rope + pos * 64 + g * 4);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float4 cs = __ldg(rp + j);     // (cos0, sin0, cos1, sin1)
+            const float x0 = x[4 * j], x1 = x[4 * j + 1], x2 = x[4 * j + 2], x3 = x[4 * j + 3];
+            x[4 * j] = cs.x * x0 - cs.y * x1;
+            x[4 * j + 1] = cs.y * x0 + cs.x * x1;
+            x[4 * j + 2] = cs.z * x2 - cs.w * x3;
+            x[4 * j + 3] = cs.w * x2 + cs.z * x3;
+          }
+        }
+      }
+      if (row_ok) st8(dst + g * 8, x);
+    }
+  } else {
+    // GELU'd MLP columns of a FLUX single block -> concat buffer
+    if (p.out8 != nullptr) {
+      // ... already quantised to MXFP8 for linear2 (its A operand): half the bytes of the bf16 store, no quantise pass
+      const long long dcol = p.out8_col_off + (ng - qkv_cols);
+      uint8_t* qrow = p.out8 + b * p.out8_bstride + static_cast<long long>(row) * p.ld8 + dcol;
+      uint32_t sfw = 0;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        float x[32];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float bv[8];
+          if (p.bias) ldg8(p.bias + ng + kb * 32 + g * 8, bv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float t = __uint_as_float(acc[kb * 32 + g * 8 + e]);
+            if (p.bias) t += bv[e];
+            x[g * 8 + e] = gelu_tanh(t);
+          }
+        }
+        sfw |= mx_quant32_store(x, qrow + kb * 32, row_ok) << (8 * kb);
+      }
+      if (row_ok) *reinterpret_cast<uint32_t*>(mx_sf_ptr(p, b, row, dcol)) = sfw;      // 4 K-blocks of one chunk
+      return;
+    }
+    const long long col = p.mlp_col_off + (ng - qkv_cols);
+    __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc + col;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[g * 8 + e]);
+      if (p.bias) {
+        float bv[8];
+        ldg8(p.bias + ng + g * 8, bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] += bv[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(x[e]);
+      if (row_ok) st8(orow + g * 8, x);
+    }
   }
 }
 
@@ -236,6 +384,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
         for (int e = 0; e < 8; ++e) a[e] = a[e] * (p.mode == EPI_GEGLU ? gelu_erf(gt[e]) : gt[e] / (1.0f + __expf(-gt[e])));
         if (row_ok) st8(orow + n / 2 + g * 8, a);
       }
+    }
+  } else if (p.mode == EPI_BIAS_GELU && p.out8 != nullptr) {
+    // GELU + MX quantisation: the 32 columns of one TMEM chunk are exactly one MX block of this thread's row
+    uint8_t* qrow = p.out8 + b * p.out8_bstride + static_cast<long long>(row) * p.ld8 + p.out8_col_off;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int n = n0 + c * 32;
+      if (n >= p.N) break;
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tmem_ld_wait();
+      float x[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float t8[8];
+        acc8(r, g, p.bias ? p.bias + n + g * 8 : nullptr, t8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[g * 8 + e] = gelu_tanh(t8[e]);
+      }
+      const uint32_t sb = mx_quant32_store(x, qrow + n, row_ok);
+      if (row_ok) *mx_sf_ptr(p, b, row, p.out8_col_off + n) = static_cast<uint8_t>(sb);
     }
   } else {
     __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc;

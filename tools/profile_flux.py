@@ -23,6 +23,7 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--fp8", action="store_true", help="MXFP8 block GEMMs (the bench default)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "profile_flux.json"))
     a = ap.parse_args()
     import torch
@@ -35,7 +36,8 @@ def main() -> int:
     torch.manual_seed(0)
     with torch.device(dev):
         model = flux.Flux(params, dtype=torch.bfloat16)
-    ex = flux_exec.FluxExecutor(model, dev)
+    ex = flux_exec.FluxExecutor(model, dev, fp8=a.fp8)
+    ex.dual_stream = False          # serialised per-op timing: keep one stream
     del model
     inp = flux.example_inputs(params, a.batch, 1024, 1024, 512, device=dev, dtype=torch.bfloat16)
     sig = torch.tensor([[1.0, 0.9]] * a.batch, device=dev)
@@ -87,8 +89,25 @@ def main() -> int:
     def ln_flop(x_, out=None, **kw):
         return 0.0, 4.0 * x_.numel()
 
+    def fp8_key(aq, sfa, wq, sfb, mode="bias", w_tile=224, **kw):
+        M = aq.numel() // aq.shape[-1]
+        return (mode, M, wq.shape[0], wq.shape[1])
+
+    def fp8_flop(aq, sfa, wq, sfb, mode="bias", w_tile=224, **kw):
+        M = aq.numel() // aq.shape[-1]
+        N, K = wq.shape
+        return 2.0 * M * N * K, 1.0 * (M * K + N * K) + 2.0 * M * N
+
+    def q_key(x_, tile_rows=128):
+        return tuple(x_.shape)
+
+    def q_flop(x_, tile_rows=128):
+        return 0.0, 3.0 * x_.numel()
+
     C = ops.require()
     ops.gemm = wrap("gemm", ops.gemm, gemm_key, gemm_flop)
+    ops.gemm_fp8 = wrap("gemm_fp8", ops.gemm_fp8, fp8_key, fp8_flop)
+    ops.quantize_mxfp8 = wrap("quantize_mxfp8", ops.quantize_mxfp8, q_key, q_flop)
     ops.attention = wrap("attention", ops.attention, attn_key, attn_flop)
     ops.layernorm_modulate = wrap("ln_mod", ops.layernorm_modulate, ln_key, ln_flop)
     orig_scatter = C.scatter_patch_embed
