@@ -1033,3 +1033,36 @@ def mxfp8_fused_quant_epilogues():
     r["ok"] = r["ok"] and r2["ok"] and r3["ok"] and r4["ok"] and max(r["mean_rel"], r2["mean_rel"], r3["mean_rel"],
                                                                    r4["mean_rel"]) < 0.035
     return r
+
+
+@check
+def groupnorm_cluster_shapes():
+    """Cluster / DSMEM GroupNorm(+SiLU) kernel across the SDXL and VAE channel counts, ragged H*W, batch 1..16 (small
+    batches split a sample's channels over several clusters), vs torch group_norm in fp32; plus its memory throughput at
+    the SDXL 128x128x320 shape (algorithmic bytes = one read + one write)."""
+    res, ok = {}, True
+    for B, C, HW, G, silu in ((1, 320, 999, 32, True), (2, 640, 1024, 32, True), (3, 960, 517, 32, False),
+                              (2, 1280, 256, 32, True), (1, 1920, 300, 32, True), (2, 2560, 64, 32, True),
+                              (2, 128, 4099, 32, True), (5, 512, 700, 32, False), (16, 320, 640, 32, True)):
+        x = _rand(B, HW, C, seed=C)
+        g, b = _rand(C, seed=1) + 1.0, _rand(C, seed=2)
+        out = ops.groupnorm_silu(x, g, b, G, 1e-5, silu)
+        want = F.group_norm(x.float().permute(0, 2, 1), G, g.float(), b.float(), 1e-5)
+        want = (F.silu(want) if silu else want).permute(0, 2, 1)
+        r = _cmp(f"gn_{B}x{HW}x{C}", out, want, 0.012)
+        res[f"{B}x{HW}x{C}"] = round(r["mean_rel"], 5)
+        ok = ok and r["ok"]
+    x = _rand(16, 16384, 320)
+    g, b = _rand(320) + 1.0, _rand(320)
+    out = torch.empty_like(x)
+    for _ in range(3):
+        ops.groupnorm_silu(x, g, b, 32, 1e-5, True, out=out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        ops.groupnorm_silu(x, g, b, 32, 1e-5, True, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    return dict(name="groupnorm_cluster_shapes", ok=bool(ok), mean_rel=res, sdxl_16x16384x320_ms=round(ms, 4),
+                algorithmic_gbs=round(2 * x.numel() * 2 / ms / 1e6, 1))

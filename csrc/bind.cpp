@@ -4,6 +4,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
+
 #include "common/host.h"
 #include "comm/scatter_params.h"
 #include "kernels/gemm_params.h"
@@ -468,6 +470,17 @@ static Tensor attention2_trace() {
 static void groupnorm_silu(Tensor x, Tensor out, Tensor gamma, Tensor beta, int groups, double eps, bool silu) {
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(x.dim() == 3 && x.is_contiguous() && out.is_contiguous(), "x must be NHWC flattened: [B, HW, C]");
+  static const bool use_cluster = []() { const char* e = std::getenv("PA_GROUPNORM_CLUSTER"); return !(e && e[0] == '0'); }();
+  if (use_cluster) {
+    // one launch: a thread-block cluster per (sample, channel slab), statistics exchanged through distributed shared memory
+    const int rc = pa::groupnorm_silu_nhwc_cluster(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                                   (int)x.size(0), (int)x.size(1), (int)x.size(2), groups, (float)eps,
+                                                   silu ? 1 : 0, cur_stream());
+    if (rc != -100) {
+      check(rc, "groupnorm_silu(cluster)");
+      return;
+    }
+  }
   Tensor ws = at::zeros({x.size(0) * groups * 2}, x.options().dtype(at::kFloat));
   check(pa::groupnorm_silu_nhwc_ws(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                    ws.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2), groups,

@@ -89,6 +89,8 @@ int attention2_debug(const void* q, const void* k, const void* v, void* out, lon
                      const long long* v_strides, float scale, cudaStream_t st);
 
 // GroupNorm (+ optional SiLU) on NHWC bf16
+int groupnorm_silu_nhwc_cluster(const void* x, void* out, const void* gamma, const void* beta, int B, int HW, int C,
+                                int groups, float eps, int apply_silu, cudaStream_t st);
 int groupnorm_silu_nhwc_ws(const void* x, void* out, const void* gamma, const void* beta, float* workspace, int B,
                            int HW, int C, int groups, float eps, int apply_silu, cudaStream_t st);
 

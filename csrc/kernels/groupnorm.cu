@@ -1,6 +1,16 @@
 // GroupNorm (+ optional fused SiLU) on channels-last bf16 activations [B, HW, C] — the layout the conv
-// implicit-GEMM consumes.  Two kernels: (1) per-(batch, group) sum / sum-of-squares with a split
-// reduction over HW (fp32 atomics into a zeroed workspace), (2) normalise + affine + SiLU, 16-byte I/O.
+// implicit-GEMM consumes.
+//
+// Default: ONE kernel, one thread-block CLUSTER of 8 CTAs per sample.  Every CTA owns a slab of HW/8 rows: pass 1
+// accumulates per-channel sum / sum-of-squares over its slab with 16-byte loads (8 channels per thread, fixed per
+// thread), folds them to per-group partials in shared memory and the 8 CTAs exchange the partials through
+// DISTRIBUTED SHARED MEMORY (cluster.map_shared_rank) - no global atomics, no zeroed workspace, no second launch;
+// pass 2 re-reads the slab (it was just streamed through L2), applies y = x * a[c] + b[c] (+ SiLU) and stores 16 bytes
+// per thread.  Profile that motivated it (profiles/r2/profile_sdxl_b16_run2.txt): the two-kernel version below ran at
+// ~1 TB/s (4-byte loads, an integer division and a rsqrt per element) and was 11 % of the SDXL step.
+// Fallback (channel counts that are not a multiple of 8, or more than 512 16-byte vectors per row): the old pair of
+// kernels - (1) per-(batch, group) sums with fp32 atomics into a zeroed workspace, (2) normalise + affine + SiLU.
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -80,6 +90,158 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat
   }
 }
 }  // namespace
+
+// ------------------------------------------------------------------ cluster kernel
+namespace {
+constexpr int GN_CS = 8;          // CTAs per cluster (= per sample); portable cluster size
+
+__global__ void __cluster_dims__(GN_CS, 1, 1) __launch_bounds__(512)
+gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                  const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta, int HW, int C, int G,
+                  int slabs, float eps, int apply_silu) {
+  // One cluster = one (sample, channel slab): a slab is a run of whole groups whose width is a multiple of 8 channels,
+  // so small batches still fill the machine (B * slabs clusters) while every thread keeps 16-byte accesses.
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  extern __shared__ float sm[];
+  const int Cs = C / slabs, Gs = G / slabs;                 // channels / groups of this slab
+  float* chs = sm;                 // [Cs] per-channel sum over this CTA's rows
+  float* chq = sm + Cs;            // [Cs] per-channel sum of squares
+  float* gpart = sm + 2 * Cs;      // [2Gs] this CTA's per-group partials (read by the other CTAs through DSMEM)
+  float* gtot = gpart + 2 * Gs;    // [2Gs] cluster totals
+  float* ca = gtot + 2 * Gs;       // [Cs]  y = x * ca + cb
+  float* cb = ca + Cs;
+  const int cl = blockIdx.x / GN_CS;
+  const int b = cl / slabs, slab = cl - b * slabs;
+  const int c0 = slab * Cs;
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int rows_per = (HW + GN_CS - 1) / GN_CS;
+  const int r0 = rank * rows_per, r1 = min(HW, r0 + rows_per);
+  const int vpr = Cs >> 3;                                  // 16-byte vectors of this slab per row
+  const int row_vecs = C >> 3;                              // row stride in vectors
+  const int lane = threadIdx.x % vpr, rsub = threadIdx.x / vpr, rp = blockDim.x / vpr;
+  const int cg = C / G;
+  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * HW * C + c0);
+  float s[8], q[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s[e] = q[e] = 0.f;
+  int r = r0 + rsub;
+  for (; r + 3 * rp < r1; r += 4 * rp) {                    // four independent 16-byte loads in flight
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(xb + static_cast<long long>(r + u * rp) * row_vecs + lane);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w0[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = bf2f(w0[e]);
+        s[2 * e] += a.x;
+        q[2 * e] = fmaf(a.x, a.x, q[2 * e]);
+        s[2 * e + 1] += a.y;
+        q[2 * e + 1] = fmaf(a.y, a.y, q[2 * e + 1]);
+      }
+    }
+  }
+  for (; r < r1; r += rp) {
+    const uint4 v0 = __ldg(xb + static_cast<long long>(r) * row_vecs + lane);
+    const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = bf2f(w0[e]);
+      s[2 * e] += a.x;
+      q[2 * e] = fmaf(a.x, a.x, q[2 * e]);
+      s[2 * e + 1] += a.y;
+      q[2 * e + 1] = fmaf(a.y, a.y, q[2 * e + 1]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(&chs[lane * 8 + e], s[e]);
+    atomicAdd(&chq[lane * 8 + e], q[e]);
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < Gs; g += blockDim.x) {
+    float gs = 0.f, gq = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      gs += chs[c];
+      gq += chq[c];
+    }
+    gpart[2 * g] = gs;
+    gpart[2 * g + 1] = gq;
+  }
+  cluster.sync();                                           // every CTA's partials are in its shared memory
+  for (int i = threadIdx.x; i < 2 * Gs; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < GN_CS; ++k) t += *cluster.map_shared_rank(gpart + i, k);      // DSMEM read of CTA k's partial
+    gtot[i] = t;
+  }
+  cluster.sync();                                           // remote reads done before any CTA may exit; gtot visible
+  const float inv_n = 1.0f / (static_cast<float>(cg) * HW);
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    const int g = c / cg;
+    const float mean = gtot[2 * g] * inv_n;
+    const float var = fmaxf(gtot[2 * g + 1] * inv_n - mean * mean, 0.f);
+    const float a = rsqrtf(var + eps) * __bfloat162float(gamma[c0 + c]);
+    ca[c] = a;
+    cb[c] = __bfloat162float(beta[c0 + c]) - mean * a;
+  }
+  __syncthreads();
+  float a8[8], b8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a8[e] = ca[lane * 8 + e];
+    b8[e] = cb[lane * 8 + e];
+  }
+  uint4* ob = reinterpret_cast<uint4*>(out + static_cast<long long>(b) * HW * C + c0);
+  for (r = r0 + rsub; r < r1; r += rp) {
+    const uint4 v0 = xb[static_cast<long long>(r) * row_vecs + lane];     // L2: this slab was streamed in pass 1
+    const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = bf2f(w0[e]);
+      float y0 = fmaf(t.x, a8[2 * e], b8[2 * e]), y1 = fmaf(t.y, a8[2 * e + 1], b8[2 * e + 1]);
+      if (apply_silu) {
+        y0 = y0 / (1.0f + __expf(-y0));
+        y1 = y1 / (1.0f + __expf(-y1));
+      }
+      o[e] = f2bf(y0, y1);
+    }
+    ob[static_cast<long long>(r) * row_vecs + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+}  // namespace
+
+// One launch, no workspace.  Returns -100 when the shape needs the two-kernel fallback.
+int groupnorm_silu_nhwc_cluster(const void* x, void* out, const void* gamma, const void* beta, int B, int HW, int C,
+                                int groups, float eps, int apply_silu, cudaStream_t st) {
+  if (C % groups) return -1;
+  if (C % 8) return -100;
+  const int cg = C / groups;
+  // channel slabs: whole groups, a multiple of 8 channels wide; as many as needed to put >= ~1 cluster CTA on every SM
+  int unit = cg;                                            // smallest legal slab width = lcm(cg, 8)
+  while (unit % 8) unit += cg;
+  if (C % unit) return -100;
+  int slabs = 1;
+  const int max_slabs = C / unit;
+  while (B * slabs * GN_CS < 148 && slabs * 2 <= max_slabs && (C / (slabs * 2)) % unit == 0) slabs *= 2;
+  if (groups % slabs) return -100;
+  const int vpr = (C / slabs) / 8;
+  if (vpr > 512 || vpr < 1) return -100;
+  const int threads = vpr * (512 / vpr);
+  const size_t smem = (4 * static_cast<size_t>(C / slabs) + 4 * static_cast<size_t>(groups / slabs)) * sizeof(float);
+  if (smem > 48 * 1024) return -100;
+  gn_cluster_kernel<<<B * slabs * GN_CS, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(x),
+                                                               static_cast<__nv_bfloat16*>(out),
+                                                               static_cast<const __nv_bfloat16*>(gamma),
+                                                               static_cast<const __nv_bfloat16*>(beta), HW, C, groups,
+                                                               slabs, eps, apply_silu);
+  return (int)cudaGetLastError();
+}
 
 // `workspace`: zeroed float[B * groups * 2]
 int groupnorm_silu_nhwc_ws(const void* x, void* out, const void* gamma, const void* beta, float* workspace, int B,

@@ -81,6 +81,32 @@ elif which == "mxfp8":
     out = torch.empty(M, N, **bf)
     for _ in range(4):
         ops.gemm_fp8(aq, sfa, wq, sfb, "bias", 224, out=out)
+elif which == "mxfp8_l1":      # FLUX single-block linear1 (one sample): drain-first QKV+RoPE epilogue, MXFP8 MLP half
+    from comfyui_parallelanything_b200.utils.selfcheck import _rope_table
+    H, L, hid, mlp = 24, 4608, 3072, 12288
+    a, w = torch.randn(1, L, hid, **bf), torch.randn(3 * hid + mlp, hid, **bf) * 0.02
+    bias = torch.randn(3 * hid + mlp, **bf)
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, sfb = ops.quantize_mxfp8(w, 256)
+    q, k, v = (torch.empty(1, H, L, 128, **bf) for _ in range(3))
+    qs, ks = torch.ones(128, **bf), torch.ones(128, **bf)
+    cat8 = torch.zeros(1, L, hid + mlp, dtype=torch.uint8, device=dev)
+    cat8_sf = torch.zeros((L // 128) * ((hid + mlp) // 128) * 512, dtype=torch.uint8, device=dev)
+    rope = torch.randn(L, 64, 2, device=dev)
+    for _ in range(4):
+        ops.gemm_fp8(aq, sfa, wq, sfb, "qkv_rope", 256, bias=bias, q=q, k=k, v=v, q_scale=qs, k_scale=ks, rope=rope,
+                     seq_off=0, out8=cat8, sf8=cat8_sf, out8_col_off=hid)
+elif which == "scatter_conv":
+    C_ = ops.require()
+    x = torch.randn(2, 4, 128, 128, **bf)
+    w4, b = torch.randn(320, 4, 3, 3, **bf) * 0.2, torch.randn(320, **bf)
+    t = torch.rand(2, **bf) * 999
+    out = torch.empty(2, 128 * 128, 320, **bf)
+    temb = torch.empty(2, 320, **bf)
+    xc = torch.empty_like(x)
+    wp = ops.pack_conv_in_weight(w4)
+    for _ in range(4):
+        C_.scatter_conv_in(wp, b, x.data_ptr(), t.data_ptr(), temb, xc, out, 4, 128, 128, 1.0, 10000.0)
 elif which == "scatter":
     C_ = ops.require()
     x = torch.randn(2, 16, 128, 128, **bf)
