@@ -894,20 +894,19 @@ def unet_executor_graph_replay():
         again = ref2.denoise_step(inp["x"], inp["timesteps"], inp["context"], inp["y"], sig).clone()
         torch.cuda.synchronize()
         scale = want.float().abs().mean().item() + 1e-6
-        # GroupNorm statistics are reduced with fp32 atomics (order varies run to run), so two EAGER executions only
-        # agree to a noise floor, measured here; the graph replay must sit within it.  A replay that missed the in-place
-        # input change / the new prompt would be off by about the step-to-step drift instead.
-        d = (got.float() - want.float()).abs().mean().item() / scale
-        nf = (again.float() - want.float()).abs().mean().item() / scale
+        # every kernel on this path is deterministic (the cluster GroupNorm folds its partial sums in a fixed order), so
+        # a graph replay must reproduce eager launches bit for bit; `drift` shows the inputs really changed between steps
+        d = (got.float() - want.float()).abs().max().item() / scale
+        nf = (again.float() - want.float()).abs().max().item() / scale
         if prev is not None:
             drift = max(drift, (want.float() - prev).abs().mean().item() / scale)
         prev = want.float()
         worst, floor = max(worst, d), max(floor, nf)
-        ok = ok and d <= 4.0 * nf + 2e-3
-    ok = ok and drift > 10.0 * worst
+        ok = ok and d == 0.0 and nf == 0.0
+    ok = ok and drift > 1e-3
     return dict(name="unet_executor_graph_replay", ok=bool(ok and len(ex._graphs) == 1 and ex._graphs.replays >= 3
                                                           and ex.fused_in),
-                mean_rel_graph_vs_eager=worst, mean_rel_eager_vs_eager=floor, step_to_step_drift=drift,
+                max_rel_graph_vs_eager=worst, max_rel_eager_vs_eager=floor, step_to_step_drift=drift,
                 captured=len(ex._graphs), replays=ex._graphs.replays, fused_conv_in=bool(ex.fused_in),
                 launches=ex.launches_per_step)
 

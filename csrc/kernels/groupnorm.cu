@@ -121,8 +121,6 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
   const int row_vecs = C >> 3;                              // row stride in vectors
   const int lane = threadIdx.x % vpr, rsub = threadIdx.x / vpr, rp = blockDim.x / vpr;
   const int cg = C / G;
-  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   const uint4* xb = reinterpret_cast<const uint4*>(x + static_cast<long long>(b) * HW * C + c0);
   float s[8], q[8];
 #pragma unroll
@@ -157,10 +155,23 @@ gn_cluster_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
       q[2 * e + 1] = fmaf(a.y, a.y, q[2 * e + 1]);
     }
   }
+  // deterministic fold over the rp row-parallel threads of every channel: partials to shared memory, fixed-order sum
+  // (no atomics anywhere in this kernel -> the same input always gives bit-identical output, unlike the fallback)
+  float* part = cb + Cs;           // [2][rp][Cs]
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    atomicAdd(&chs[lane * 8 + e], s[e]);
-    atomicAdd(&chq[lane * 8 + e], q[e]);
+    part[rsub * Cs + lane * 8 + e] = s[e];
+    part[(rp + rsub) * Cs + lane * 8 + e] = q[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cs; c += blockDim.x) {
+    float ts = 0.f, tq = 0.f;
+    for (int k = 0; k < rp; ++k) {
+      ts += part[k * Cs + c];
+      tq += part[(rp + k) * Cs + c];
+    }
+    chs[c] = ts;
+    chq[c] = tq;
   }
   __syncthreads();
   for (int g = threadIdx.x; g < Gs; g += blockDim.x) {
@@ -233,7 +244,9 @@ int groupnorm_silu_nhwc_cluster(const void* x, void* out, const void* gamma, con
   const int vpr = (C / slabs) / 8;
   if (vpr > 512 || vpr < 1) return -100;
   const int threads = vpr * (512 / vpr);
-  const size_t smem = (4 * static_cast<size_t>(C / slabs) + 4 * static_cast<size_t>(groups / slabs)) * sizeof(float);
+  const int rp = threads / vpr;
+  const size_t smem = (4 * static_cast<size_t>(C / slabs) + 4 * static_cast<size_t>(groups / slabs) +
+                       2 * static_cast<size_t>(rp) * (C / slabs)) * sizeof(float);
   if (smem > 48 * 1024) return -100;
   gn_cluster_kernel<<<B * slabs * GN_CS, threads, smem, st>>>(static_cast<const __nv_bfloat16*>(x),
                                                                static_cast<__nv_bfloat16*>(out),

@@ -107,6 +107,67 @@ elif which == "scatter_conv":
     wp = ops.pack_conv_in_weight(w4)
     for _ in range(4):
         C_.scatter_conv_in(wp, b, x.data_ptr(), t.data_ptr(), temb, xc, out, 4, 128, 128, 1.0, 10000.0)
+elif which in ("scatter_peer", "gather_peer", "scatter_conv_peer"):
+    # ONE process, two GPUs: the kernel runs on cuda:1, the lead's buffers live on cuda:0 (NVLink peer mapping), exactly
+    # what a non-lead replica of the in-process engine does every step.  Capture with the NVLink byte counters.
+    C_ = ops.require()
+    assert torch.cuda.device_count() >= 2, "needs 2 GPUs"
+    C_.enable_peer_access(1, 0)
+    d0, d1 = torch.device("cuda:0"), torch.device("cuda:1")
+    n = 4
+    torch.cuda.set_device(d1)
+    if which == "scatter_peer":
+        x0 = torch.randn(n, 16, 128, 128, dtype=torch.bfloat16, device=d0)
+        t0 = torch.rand(n, dtype=torch.bfloat16, device=d0)
+        w, b = torch.randn(3072, 64, dtype=torch.bfloat16, device=d1) * 0.1, torch.randn(3072, dtype=torch.bfloat16, device=d1)
+        X = torch.empty(n, 4608, 3072, dtype=torch.bfloat16, device=d1)
+        te, ge = (torch.empty(n, 256, dtype=torch.bfloat16, device=d1) for _ in range(2))
+        xc = torch.empty(n, 16, 128, 128, dtype=torch.bfloat16, device=d1)
+        torch.cuda.synchronize(d0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(6):
+            if i == 3:
+                ev[0].record()
+            C_.scatter_patch_embed(w, b, x0.data_ptr(), t0.data_ptr(), t0.data_ptr(), te, ge, xc, X[:, 512:], 16, 128, 128, 1000.0)
+        ev[1].record()
+        torch.cuda.synchronize(d1)
+        print("scatter_peer us/launch", ev[0].elapsed_time(ev[1]) / 3 * 1e3, "peer bytes/launch", x0.numel() * 2,
+              "copy ok", bool(torch.equal(xc.cpu(), x0.cpu())))
+    elif which == "scatter_conv_peer":
+        x0 = torch.randn(n, 4, 128, 128, dtype=torch.bfloat16, device=d0)
+        t0 = (torch.rand(n, device=d0) * 999).to(torch.bfloat16)
+        wp = ops.pack_conv_in_weight(torch.randn(320, 4, 3, 3, dtype=torch.bfloat16, device=d1) * 0.2)
+        b = torch.randn(320, dtype=torch.bfloat16, device=d1)
+        out = torch.empty(n, 128 * 128, 320, dtype=torch.bfloat16, device=d1)
+        temb = torch.empty(n, 320, dtype=torch.bfloat16, device=d1)
+        xc = torch.empty(n, 4, 128, 128, dtype=torch.bfloat16, device=d1)
+        torch.cuda.synchronize(d0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(6):
+            if i == 3:
+                ev[0].record()
+            C_.scatter_conv_in(wp, b, x0.data_ptr(), t0.data_ptr(), temb, xc, out, 4, 128, 128, 1.0, 10000.0)
+        ev[1].record()
+        torch.cuda.synchronize(d1)
+        print("scatter_conv_peer us/launch", ev[0].elapsed_time(ev[1]) / 3 * 1e3, "peer bytes/launch", x0.numel() * 2,
+              "copy ok", bool(torch.equal(xc.cpu(), x0.cpu())))
+    else:
+        out0 = torch.zeros(n, 16, 128, 128, dtype=torch.bfloat16, device=d0)
+        xm = torch.randn(n, 4096, 3072, dtype=torch.bfloat16, device=d1)
+        wf, bfin = torch.randn(64, 3072, dtype=torch.bfloat16, device=d1) * 0.02, torch.randn(64, dtype=torch.bfloat16, device=d1)
+        x1 = torch.randn(n, 16, 128, 128, dtype=torch.bfloat16, device=d1)
+        sig = torch.tensor([[1.0, 0.9]] * n, device=d1)
+        torch.cuda.synchronize(d0)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(6):
+            if i == 3:
+                ev[0].record()
+            ops.gemm(xm, wf, "euler_unpatch", bias=bfin, C=16, Hl=128, Wl=128, xout_sample_off=0, x_out_ptr=out0.data_ptr(),
+                     sigmas=sig, x_in=x1)
+        ev[1].record()
+        torch.cuda.synchronize(d1)
+        print("gather_peer us/launch", ev[0].elapsed_time(ev[1]) / 3 * 1e3, "peer bytes/launch", out0.numel() * 2,
+              "finite", bool(torch.isfinite(out0.float()).all()))
 elif which == "scatter":
     C_ = ops.require()
     x = torch.randn(2, 16, 128, 128, **bf)
