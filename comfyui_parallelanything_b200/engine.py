@@ -36,7 +36,7 @@ from . import chain as chain_mod
 from . import exec as native_exec
 from .parallel import pipeline as pp
 from .parallel import split as sp
-from .parallel.workers import WorkerPool
+from .parallel.workers import WorkerPool, device_scope
 from .utils import dtypes, faults, log, memory, replicate
 from .utils.config import EngineConfig
 
@@ -434,6 +434,9 @@ class ParallelEngine:
                         if slot.stream is not None and lead_stream is not None and lead_dev == dev:
                             lead_stream.wait_stream(slot.stream)
                         return r
+            if dev.type == "xpu":
+                with device_scope(dev):                 # torch.xpu.device(dev) + sync before/after (ADP:1398-1403)
+                    return body()
             return body()
 
         futures = [active[i][0].worker.submit(lambda i=i: run(i)) for i in range(len(active))]

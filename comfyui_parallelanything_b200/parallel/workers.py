@@ -17,6 +17,50 @@ from typing import Any, Callable, List, Optional
 import torch
 
 
+class device_scope:
+    """``with device_scope(dev):`` - make ``dev`` the current device of its backend for the duration of a replica's
+    forward and, for backends whose queues we do not order with streams/events (XPU), bracket the work with the
+    backend's synchronize - the reference's per-backend branches (/root/reference/any_device_parallel.py:1385-1406:
+    cuda -> device + stream, xpu -> ``torch.xpu.device(dev)`` + two syncs, cpu / mps -> plain call)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self._ctx = None
+
+    def _backend(self):
+        return getattr(torch, self.device.type, None) if self.device.type in ("cuda", "xpu") else None
+
+    def __enter__(self):
+        be = self._backend()
+        if be is not None and hasattr(be, "device"):
+            self._ctx = be.device(self.device)
+            self._ctx.__enter__()
+            if self.device.type == "xpu" and hasattr(be, "synchronize"):
+                be.synchronize(self.device)
+        return self
+
+    def __exit__(self, *exc):
+        be = self._backend()
+        try:
+            if self.device.type == "xpu" and be is not None and hasattr(be, "synchronize") and exc[0] is None:
+                be.synchronize(self.device)
+        finally:
+            if self._ctx is not None:
+                self._ctx.__exit__(*exc)
+        return False
+
+
+def set_thread_device(device) -> None:
+    """Pin a worker thread to its device once (cuda and xpu keep a per-thread current device)."""
+    device = torch.device(device)
+    be = getattr(torch, device.type, None) if device.type in ("cuda", "xpu") else None
+    if be is not None and hasattr(be, "set_device"):
+        try:
+            be.set_device(device)
+        except Exception:
+            pass
+
+
 class DeviceWorker:
     def __init__(self, index: int, device: torch.device, stream: Optional["torch.cuda.Stream"] = None):
         self.index = index
@@ -28,11 +72,7 @@ class DeviceWorker:
         self._thread.start()
 
     def _run(self) -> None:
-        if self.device.type == "cuda":
-            try:
-                torch.cuda.set_device(self.device)
-            except Exception:
-                pass
+        set_thread_device(self.device)
         while True:
             item = self._q.get()
             if item is None:

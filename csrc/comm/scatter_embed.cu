@@ -24,12 +24,15 @@ namespace se {
 constexpr int BM = 128, BN = 256, BK = 64, WSTAGES = 3;
 constexpr uint32_t A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
 constexpr uint32_t OFF_W = A_BYTES;
-constexpr uint32_t OFF_BAR = OFF_W + WSTAGES * W_BYTES;
+constexpr uint32_t OFF_STAGE = OFF_W + WSTAGES * W_BYTES;      // 4 slabs of [128 rows x 64 cols] bf16, 128B-swizzled
+constexpr uint32_t STAGE_BYTES = BM * BN * 2;
+constexpr uint32_t OFF_BAR = OFF_STAGE + STAGE_BYTES;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 256 + 1024;
 }  // namespace se
 
 __global__ void __launch_bounds__(256, 1)
-scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const ScatterEmbedParams p) {
+scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmO,
+                           const ScatterEmbedParams p) {
   using namespace se;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -48,7 +51,10 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
   const int tok0 = (blockIdx.x - b * m_per) * BM;
   const int num_n = (p.N + BN - 1) / BN;
 
-  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmW);
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmO);
+  }
   if (warp == 1 && lane == 0) {
     ptx::mbar_init(a_full, 128);
     for (int s = 0; s < WSTAGES; ++s) {
@@ -155,9 +161,12 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
     }
     ptx::fence_proxy_async_smem();
     ptx::mbar_arrive(a_full);
-    // ---- epilogue: bias + bf16 store of the residual-stream rows
-    const bool row_ok = tok < p.Li;
-    __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(tok) * p.ldo;
+    // ---- epilogue: bias -> bf16 -> 128B-swizzled shared-memory staging -> TMA store.  A thread owns one accumulator
+    // ROW, so storing straight to global memory makes every warp-level store touch 32 different 128-byte lines (16
+    // useful bytes each); staged through shared memory the tile leaves the SM as whole 128-byte rows of a bulk tensor
+    // store (UTMASTG), rows past the end of the sample are clipped by the tensor map.
+    uint8_t* stage = smem + OFF_STAGE;
+    const uint32_t stage_u = ptx::smem_u32(stage);
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(q4 * 32) << 16);
     for (int nt = 0; nt < num_n; ++nt) {
       const int acc = nt & 1;
@@ -170,6 +179,7 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
         uint32_t t[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + acc * BN + c * 32, t);
         ptx::tmem_ld_wait();
+        uint8_t* srow = stage + (c >> 1) * (BM * 128) + r * 128;          // slab of 64 columns, this thread's row
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint4 bu = __ldg(reinterpret_cast<const uint4*>(p.bias + n + g * 8));
@@ -183,12 +193,24 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const Scatte
                                                       __uint_as_float(t[g * 8 + 2 * e + 1]) + bf.y);
             o[e] = *reinterpret_cast<uint32_t*>(&ov);
           }
-          if (row_ok) *reinterpret_cast<uint4*>(orow + n + g * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          const int chunk = ((c & 1) * 4 + g) ^ sw;                        // 16-byte chunk inside the 128-byte row
+          *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+      // accumulator drained: hand it back to the MMA warp before the (asynchronous) store
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);                                         // all 128 rows of the tile are staged
+      if (warp == 4 && ptx::elect_one()) {
+#pragma unroll
+        for (int sl = 0; sl < BN / 64; ++sl)
+          if (nt * BN + sl * 64 < p.N) ptx::tma_store_3d(&tmO, stage_u + sl * (BM * 128), nt * BN + sl * 64, tok0, b);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read<0>();                                     // staging may be overwritten afterwards
+      }
+      ptx::named_bar_sync(1, 128);
     }
   }
 
@@ -208,6 +230,14 @@ int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& 
   uint64_t str[2] = {2, (uint64_t)ldw * 2};
   uint32_t box[2] = {64, (uint32_t)BN};
   if (make_tmap(&tw, W, 2, dims, str, box, 2)) return -20;
+  CUtensorMap to;                                   // output rows X[b, Lt + token, :] for the epilogue's TMA stores
+  {
+    uint64_t od[3] = {(uint64_t)p.N, (uint64_t)p.Li, (uint64_t)p.n};
+    uint64_t os[3] = {2, (uint64_t)p.ldo * 2, (uint64_t)p.out_bstride * 2};
+    uint32_t ob[3] = {64, (uint32_t)BM, 1};
+    if ((p.ldo % 8) || (p.out_bstride % 8) || (reinterpret_cast<uintptr_t>(p.out) & 15)) return -2;
+    if (make_tmap(&to, p.out, 3, od, os, ob, 2)) return -21;
+  }
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -218,7 +248,7 @@ int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& 
     attr_set[dev] = true;
   }
   const int grid = p.n * ((p.Li + BM - 1) / BM);
-  scatter_patch_embed_kernel<<<grid, 256, SMEM_BYTES, st>>>(tw, p);
+  scatter_patch_embed_kernel<<<grid, 256, SMEM_BYTES, st>>>(tw, to, p);
   return (int)cudaGetLastError();
 }
 

@@ -273,3 +273,45 @@ def test_small_batch_spreads_over_devices():
     assert m.calls == [1, 1, 1]
     assert m._parallel_engine.metrics.counters.get("small_batch_spread_steps") == 1
     pa.cleanup_parallel_model(m)
+
+
+def test_xpu_device_scope_matches_reference_branch(monkeypatch):
+    """ADP:1398-1403: an XPU replica runs under ``torch.xpu.device(dev)`` with a synchronize before and after; cuda gets
+    its device context only (ordering is done with streams / events), cpu nothing."""
+    from comfyui_parallelanything_b200.parallel import workers
+    calls = []
+
+    class FakeCtx:
+        def __init__(self, d):
+            self.d = d
+
+        def __enter__(self):
+            calls.append(("enter", str(self.d)))
+
+        def __exit__(self, *a):
+            calls.append(("exit", str(self.d)))
+
+    class FakeXpu:
+        @staticmethod
+        def device(d):
+            return FakeCtx(d)
+
+        @staticmethod
+        def synchronize(d):
+            calls.append(("sync", str(d)))
+
+        @staticmethod
+        def set_device(d):
+            calls.append(("set", str(d)))
+
+    monkeypatch.setattr(torch, "xpu", FakeXpu, raising=False)
+    with workers.device_scope("xpu:1"):
+        calls.append(("body", ""))
+    assert calls == [("enter", "xpu:1"), ("sync", "xpu:1"), ("body", ""), ("sync", "xpu:1"), ("exit", "xpu:1")]
+    calls.clear()
+    workers.set_thread_device("xpu:0")
+    assert calls == [("set", "xpu:0")]
+    calls.clear()
+    with workers.device_scope("cpu"):
+        pass
+    assert calls == []
