@@ -85,6 +85,7 @@ class ParallelEngine:
         self._native_shells: List[Any] = []    # executors of the same geometry on other GPUs, filled over NVLink
         self.setup_report: Dict[str, Any] = {}
         self._host_exec = None                 # native per-GPU launcher threads (csrc/runtime HostExecutor)
+        self._ulysses = None                   # sequence-parallel batch-1 path (exec/flux_sp.py), native FLUX replicas only
         self.active = False
 
     # ------------------------------------------------------------------ setup
@@ -224,6 +225,18 @@ class ParallelEngine:
             log.warn("peer access could not be enabled (%s); using copy-based scatter/gather", e)
             ok = False
         self._peer_ready = bool(ok) and len(native) == len(self.slots)
+        if self._peer_ready and self.config.batch1_mode in ("auto", "ulysses") and self.config.workload_split:
+            from .exec import flux_sp
+            why = flux_sp.supported([s.replica for s in self.slots])
+            if why is None:
+                try:
+                    self._ulysses = flux_sp.FluxUlysses([s.replica for s in self.slots],
+                                                        timeout_ms=self.config.flag_timeout_ms)
+                    log.info("batch=1 will run sequence-parallel (Ulysses) over %d GPUs", len(self.slots))
+                except Exception as e:
+                    log.warn("sequence-parallel batch=1 path unavailable: %s", e)
+            elif self.config.batch1_mode == "ulysses":
+                log.warn("PA_BATCH1=ulysses requested but %s; using the layer-split mode", why)
         if self._peer_ready and self.config.host_threads and self.config.cuda_graphs:
             try:
                 self._host_exec = C.HostExecutor([s.device.index for s in self.slots])
@@ -295,6 +308,9 @@ class ParallelEngine:
         try:
             batch = sp.get_batch_size(x)
             n = len(self.slots)
+            if batch == 1 and self.config.workload_split and self._ulysses is not None \
+                    and self._can_ulysses(x, timesteps, context):
+                return self._forward_ulysses(step, x, timesteps, context, kwargs)
             if batch == 1 and self.config.workload_split:
                 with pp.pipeline_mode(True):
                     lead = self.slots[0]
@@ -592,6 +608,101 @@ class ParallelEngine:
         res = out.clone()
         return res if x.dtype == res.dtype else res.to(x.dtype)
 
+    # ---- batch == 1: sequence-parallel (Ulysses) over all native FLUX replicas --------------------------------------
+    def _can_ulysses(self, x, timesteps, context) -> bool:
+        if not (isinstance(x, torch.Tensor) and isinstance(context, torch.Tensor) and isinstance(timesteps, torch.Tensor)):
+            return False
+        if x.device != self.lead_device or x.dim() != 4 or not x.is_floating_point():
+            return False
+        n = len(self.slots)
+        H, Wd, Lt = x.shape[2], x.shape[3], context.shape[1]
+        return H % 2 == 0 and Wd % 2 == 0 and Lt % n == 0 and ((H // 2) * (Wd // 2)) % n == 0 and Lt >= n
+
+    def _forward_ulysses(self, step, x, timesteps, context, kwargs):
+        """One sample, every GPU of the chain: token-sliced linear layers, head-sliced attention, peer-pull all-to-all
+        (exec/flux_sp.py).  Inputs are staged into fixed buffers (a sampler passes fresh tensors), each GPU's share of
+        the step is one CUDA graph; the velocity rows land in the lead GPU's output buffer through the fused gather."""
+        sp = self._ulysses
+        lead_dev = self.lead_device
+        lead_stream = torch.cuda.current_stream(lead_dev)
+        y, guidance = kwargs.get("y"), kwargs.get("guidance")
+        bf = torch.bfloat16
+        key = ("sp", tuple(x.shape), tuple(context.shape), None if y is None else tuple(y.shape), guidance is not None)
+        io = self._io.get(key)
+        if io is None:
+            io = {"x": torch.empty(tuple(x.shape), dtype=bf, device=lead_dev),
+                  "out": torch.empty(tuple(x.shape), dtype=bf, device=lead_dev), "slots": []}
+            ex0 = self.slots[0].replica
+            for slot in self.slots:
+                d = slot.device
+                io["slots"].append({
+                    "t": torch.empty(1, dtype=bf, device=d), "ctx": torch.empty(tuple(context.shape), dtype=bf, device=d),
+                    "y": torch.zeros(1, ex0.params.vec_in_dim, dtype=bf, device=d),
+                    "g": torch.ones(1, dtype=bf, device=d), "ctx_src": None})
+            if len(self._io) >= 8:
+                self._io.pop(next(iter(self._io)))
+            self._io[key] = io
+        t0 = time.perf_counter()
+        xs, out = io["x"], io["out"]
+        xs.copy_(x, non_blocking=True)
+        wss = sp.workspace(x.shape[2], x.shape[3], context.shape[1])
+        for slot, st in zip(self.slots, io["slots"]):
+            with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream):
+                slot.stream.wait_stream(lead_stream)
+                st["t"].copy_(timesteps.reshape(-1)[:1], non_blocking=True)
+                ident = (id(context), context.data_ptr(), context._version)
+                if not self.config.cache_conditioning or st["ctx_src"] is None or st["ctx_src"][0] != ident:
+                    st["ctx"].copy_(context, non_blocking=True)
+                    st["ctx_src"] = (ident, context)
+                if y is not None:
+                    st["y"].copy_(y[:, :st["y"].shape[1]], non_blocking=True)
+                if guidance is not None:
+                    st["g"].copy_(guidance.reshape(-1)[:1], non_blocking=True)
+        ge = self.slots[0].replica.params.guidance_embed
+        if ge and guidance is None:
+            raise ValueError("guidance-distilled model needs a guidance strength")
+        gkey = ("sp",) + key[1:]
+
+        def body(g):
+            st = io["slots"][g]
+            sp.run_rank(g, wss, xs.data_ptr(), st["t"], st["ctx"], st["y"], st["g"] if ge else None, out.data_ptr())
+
+        launched = False
+        if self._host_exec is not None:
+            handles = [s.replica._graphs.exec_handle(gkey) for s in self.slots]
+            if all(handles):
+                for s, h in zip(self.slots, handles):
+                    self._host_exec.launch_graph(s.index, h, s.stream.cuda_stream)
+                self._host_exec.sync()
+                for s in self.slots:
+                    lead_stream.wait_stream(s.stream)
+                self.metrics.incr("native_graph_steps")
+                launched = True
+        if not launched:
+            def run(g: int):
+                slot = self.slots[g]
+                pp.set_pipeline_mode(False)
+                faults.check_step(step, slot.name, slot.index)
+                with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
+                    slot.replica._graphs.run(gkey, lambda: body(g))
+                    lead_stream.wait_stream(slot.stream)
+            futures = [self.slots[g].worker.submit(lambda g=g: run(g)) for g in range(len(self.slots))]
+            errors = []
+            for g, f in enumerate(futures):
+                try:
+                    f.result()
+                except BaseException as e:  # noqa: BLE001
+                    errors.append((self.slots[g].name, e))
+            if errors:
+                for name, e in errors:
+                    log.error("on %s: %s", name, e)
+                raise errors[0][1]
+        self.metrics.incr("ulysses_steps")
+        self.metrics.record(step=step, host_ms=(time.perf_counter() - t0) * 1e3, batch=1, sizes=[1], ulysses=True,
+                            native_launch=launched)
+        res = out.clone()
+        return res if x.dtype == res.dtype else res.to(x.dtype)
+
     def _cached_move(self, key, value, dev):
         """Conditioning is constant across the steps of one sampling run; re-use the
         device copy while the source tensor object/version is unchanged."""
@@ -648,6 +759,9 @@ class ParallelEngine:
                 pass
             self._host_exec = None
         self._io.clear()
+        if self._ulysses is not None:
+            self._ulysses.release()
+            self._ulysses = None
         self._cond_cache.clear()
         self._drop_replicas()
         self.slots = []

@@ -8,6 +8,7 @@
 
 #include "common/host.h"
 #include "comm/scatter_params.h"
+#include "comm/sp_params.h"
 #include "kernels/gemm_params.h"
 #include "runtime/runtime.h"
 
@@ -160,11 +161,16 @@ static void parse_modes(int mode, const py::kwargs& kw, pa::GemmParams& p) {
                   "rope must be float32 [L, 64, 2]");
       p.rope = reinterpret_cast<const float2*>(r.data_ptr());
     }
+    p.rope_off = has(kw, "rope_off") ? kw["rope_off"].cast<int>() : 0;
+    p.rope_off2 = has(kw, "rope_off2") ? kw["rope_off2"].cast<int>() : p.rope_off;
+    p.seg_rows = has(kw, "seg_rows") ? kw["seg_rows"].cast<int>() : 0;
+    if (!has(kw, "seg_rows")) p.rope_off2 = p.rope_off;         // one segment: every row uses rope_off
     p.mlp_cols = p.N - 3 * p.heads * 128;
     p.mlp_col_off = has(kw, "mlp_col_off") ? kw["mlp_col_off"].cast<long long>() : 0;
     TORCH_CHECK(p.mlp_cols == 0 || p.out != nullptr || p.out8 != nullptr, "single-block QKV+MLP needs out= or out8=");
   }
   if (mode == pa::EPI_EULER_UNPATCH) {
+    p.tok_off = has(kw, "tok_off") ? kw["tok_off"].cast<int>() : 0;
     p.C = kw["C"].cast<int>();
     p.Hl = kw["Hl"].cast<int>();
     p.Wl = kw["Wl"].cast<int>();
@@ -500,6 +506,31 @@ static void cfg_euler_store(Tensor x, Tensor eps_c, c10::optional<Tensor> eps_u,
         "cfg_euler_store");
 }
 
+// ---- sequence-parallel (Ulysses) exchange: flags with device-resident epochs + table-driven peer pull
+static void sp_signal(Tensor peer_flag_table, int n_peers, int slot, int me, Tensor epoch) {
+  c10::cuda::CUDAGuard guard(peer_flag_table.device());
+  check(pa::sp_signal(reinterpret_cast<uint32_t* const*>(peer_flag_table.data_ptr()), n_peers, slot, me,
+                      reinterpret_cast<const uint32_t*>(epoch.data_ptr()), cur_stream()),
+        "sp_signal");
+}
+
+static void sp_pull(Tensor descs, int n_desc, int blocks_per_desc, Tensor flags, int slot, int n_peers, Tensor epoch,
+                    long long timeout_cycles, Tensor err) {
+  c10::cuda::CUDAGuard guard(descs.device());
+  TORCH_CHECK(descs.is_contiguous() && descs.numel() * descs.element_size() >= (int64_t)n_desc * (int64_t)sizeof(pa::SpPullDesc),
+              "descriptor table too small");
+  check(pa::sp_pull(reinterpret_cast<const pa::SpPullDesc*>(descs.data_ptr()), n_desc, blocks_per_desc,
+                    reinterpret_cast<const uint32_t*>(flags.data_ptr()), slot, n_peers,
+                    reinterpret_cast<const uint32_t*>(epoch.data_ptr()), timeout_cycles,
+                    reinterpret_cast<uint32_t*>(err.data_ptr()), cur_stream()),
+        "sp_pull");
+}
+
+static void sp_epoch_inc(Tensor epoch) {
+  c10::cuda::CUDAGuard guard(epoch.device());
+  check(pa::sp_epoch_inc(reinterpret_cast<uint32_t*>(epoch.data_ptr()), cur_stream()), "sp_epoch_inc");
+}
+
 static void signal_flags(Tensor peer_ptr_table, int n_peers, int slot, uint32_t value) {
   c10::cuda::CUDAGuard guard(peer_ptr_table.device());
   check(pa::signal_flags(reinterpret_cast<uint32_t* const*>(peer_ptr_table.data_ptr()), n_peers, slot, value,
@@ -549,6 +580,12 @@ PYBIND11_MODULE(_C, m) {
         py::arg("eps") = 1e-5, py::arg("tanh_gate") = true);
   m.def("groupnorm_silu", &groupnorm_silu);
   m.def("cfg_euler_store", &cfg_euler_store);
+  m.def("sp_signal", &sp_signal);
+  m.def("sp_pull", &sp_pull);
+  m.def("sp_epoch_inc", &sp_epoch_inc);
+  m.attr("SP_MAX_RANKS") = (int)pa::SP_MAX_RANKS;
+  m.attr("SP_MAX_SLOTS") = (int)pa::SP_MAX_SLOTS;
+  m.attr("SP_DESC_BYTES") = (int)sizeof(pa::SpPullDesc);
   m.def("signal_flags", &signal_flags);
   m.def("wait_flags", &wait_flags);
   m.def("num_sms", &pa::num_sms);

@@ -46,10 +46,18 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // provably warp-uniform role index
+  // grid = samples x token tiles x N-splits: with one sample per rank (8-GPU runs) 32 token tiles alone would leave
+  // 3/4 of the SMs idle and serialise 12 weight tiles per CTA, so the output columns are split over `nsplit` CTAs
+  // (each re-gathers the same 128 tokens: 16 KB of peer loads, L1-cached per SM)
   const int m_per = (p.Li + BM - 1) / BM;
-  const int b = blockIdx.x / m_per;
-  const int tok0 = (blockIdx.x - b * m_per) * BM;
-  const int num_n = (p.N + BN - 1) / BN;
+  const int nsplit = p.nsplit;
+  const int mb = blockIdx.x / nsplit, ns_i = blockIdx.x - mb * nsplit;
+  const int b = mb / m_per;
+  const int tok0 = (mb - b * m_per) * BM;
+  const int num_n_all = (p.N + BN - 1) / BN;
+  const int n_per = (num_n_all + nsplit - 1) / nsplit;
+  const int nt0 = ns_i * n_per;
+  const int num_n = max(0, min(num_n_all, nt0 + n_per) - nt0);      // this CTA's weight tiles: nt0 .. nt0 + num_n
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmW);
@@ -84,7 +92,7 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
       ptx::mbar_wait(&w_empty[s], ph ^ 1);
       if (leader) {
         ptx::mbar_arrive_expect_tx(&w_full[s], W_BYTES);
-        ptx::tma_load_2d_s(smem_u + OFF_W + s * W_BYTES, &tmW, &w_full[s], 0, nt * BN);
+        ptx::tma_load_2d_s(smem_u + OFF_W + s * W_BYTES, &tmW, &w_full[s], 0, (nt0 + nt) * BN);
       }
     }
     __syncwarp();
@@ -141,18 +149,26 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
       const int hh = tok / Wp, ww = tok - hh * Wp;
       const long long sample = static_cast<long long>(b) * p.C * p.Hl * p.Wl;
       const __nv_bfloat16* xs = p.x_src + sample;
-#pragma unroll 4
+      // all 32 peer loads are issued before the first use: one NVLink round trip (~2-3 us) instead of four
+      uint32_t v[32];
+#pragma unroll
       for (int c = 0; c < 16; ++c) {
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
           const long long pix = (static_cast<long long>(c) * p.Hl + (hh * 2 + ph)) * p.Wl + ww * 2;
-          uint32_t v = 0;
-          if (c < p.C) {
-            v = *reinterpret_cast<const uint32_t*>(xs + pix);
-            if (p.x_copy) *reinterpret_cast<uint32_t*>(p.x_copy + sample + pix) = v;
+          v[c * 2 + ph] = c < p.C ? *reinterpret_cast<const uint32_t*>(xs + pix) : 0u;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          if (p.x_copy && ns_i == 0 && c < p.C) {
+            const long long pix = (static_cast<long long>(c) * p.Hl + (hh * 2 + ph)) * p.Wl + ww * 2;
+            *reinterpret_cast<uint32_t*>(p.x_copy + sample + pix) = v[c * 2 + ph];
           }
           const int chunk = (c >> 1) ^ sw;
-          *reinterpret_cast<uint32_t*>(arow + chunk * 16 + (c & 1) * 8 + ph * 4) = v;
+          *reinterpret_cast<uint32_t*>(arow + chunk * 16 + (c & 1) * 8 + ph * 4) = v[c * 2 + ph];
         }
       }
     } else {
@@ -174,7 +190,7 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
-        const int n = nt * BN + c * 32;
+        const int n = (nt0 + nt) * BN + c * 32;
         if (n >= p.N) break;
         uint32_t t[32];
         ptx::tmem_ld_32x32b_x32(lane_addr + acc * BN + c * 32, t);
@@ -206,7 +222,8 @@ scatter_patch_embed_kernel(const __grid_constant__ CUtensorMap tmW, const __grid
       if (warp == 4 && ptx::elect_one()) {
 #pragma unroll
         for (int sl = 0; sl < BN / 64; ++sl)
-          if (nt * BN + sl * 64 < p.N) ptx::tma_store_3d(&tmO, stage_u + sl * (BM * 128), nt * BN + sl * 64, tok0, b);
+          if ((nt0 + nt) * BN + sl * 64 < p.N)
+            ptx::tma_store_3d(&tmO, stage_u + sl * (BM * 128), (nt0 + nt) * BN + sl * 64, tok0, b);
         ptx::tma_store_commit();
         ptx::tma_store_wait_read<0>();                                     // staging may be overwritten afterwards
       }
@@ -247,8 +264,12 @@ int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& 
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
-  const int grid = p.n * ((p.Li + BM - 1) / BM);
-  scatter_patch_embed_kernel<<<grid, 256, SMEM_BYTES, st>>>(tw, to, p);
+  ScatterEmbedParams q = p;
+  const int mtiles = p.n * ((p.Li + BM - 1) / BM);
+  const int num_n = (p.N + BN - 1) / BN;
+  q.nsplit = 1;
+  while (mtiles * q.nsplit * 2 <= 160 && q.nsplit * 2 <= num_n) q.nsplit *= 2;      // fill ~148 SMs, whole tiles per CTA
+  scatter_patch_embed_kernel<<<mtiles * q.nsplit, 256, SMEM_BYTES, st>>>(tw, to, q);
   return (int)cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@ struct ScatterEmbedParams {
   const __nv_bfloat16* bias;      // [N]
   int n, C, Hl, Wl, N, Li;
   float time_factor;
+  int nsplit;                     // CTAs sharing one token tile, each owning a slice of the N weight tiles (set by the launcher)
 };
 
 }  // namespace pa

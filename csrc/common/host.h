@@ -14,6 +14,11 @@ int scatter_conv_in(const void* W, long long ldw, const ScatterConvParams& p, cu
 int scatter_patch_embed(const void* W, long long ldw, const ScatterEmbedParams& p, cudaStream_t st);
 
 int multimem_bcast(const void* src, void* mc_dst, long long bytes, cudaStream_t st);
+struct SpPullDesc;
+int sp_signal(uint32_t* const* peer_flags, int n_peers, int slot, int me, const uint32_t* epoch, cudaStream_t st);
+int sp_pull(const SpPullDesc* descs, int n_desc, int blocks_per_desc, const uint32_t* flags, int slot, int n_peers,
+            const uint32_t* epoch, long long timeout, uint32_t* err, cudaStream_t st);
+int sp_epoch_inc(uint32_t* epoch, cudaStream_t st);
 int num_sms();
 void set_sm_limit(int n);   // per-thread SM budget for persistent-kernel grids (0 = all)
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

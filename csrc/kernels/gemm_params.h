@@ -44,6 +44,9 @@ struct GemmParams {
   const __nv_bfloat16 *q_scale, *k_scale;   // [128] RMSNorm weights
   const float2* rope;               // [seq_total, 64] (cos, sin); nullptr = no rope
   int heads, seq_off, seq_total;
+  // RoPE row = destination row + rope_off (rows < seg_rows) or + rope_off2 (rows >= seg_rows): sequence-parallel replicas
+  // keep a LOCAL [txt slice | img slice] token layout whose global positions are two separate ranges
+  int rope_off, rope_off2, seg_rows;
   int mlp_cols;                     // columns after the 3*H*128 qkv columns (FLUX single blocks)
   long long mlp_col_off;            // where they start inside `out`
   float qk_eps;
@@ -53,6 +56,7 @@ struct GemmParams {
   long long xout_sample_off;        // first sample of this rank inside x_out
   const float* sigmas;              // [batch, 2] (sigma, sigma_next) per sample, or nullptr => out = v
   int C, Hl, Wl, ps;
+  int tok_off;                      // EULER_UNPATCH: global token index of row 0 (sequence-parallel replicas own a token range)
   // implicit-GEMM convolution: A is an NHWC activation addressed through a 4-D TMA tensor
   // (C, W, H, N); the K loop walks taps x Cin-blocks with shifted spatial coordinates, padding
   // comes from TMA out-of-bounds zero fill.  rows = Ho*Wo, batch = N.

@@ -180,7 +180,7 @@ __device__ __forceinline__ void epilogue_qkv_from_regs(const GemmParams& p, cons
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = x[e] * rrms * w[e];
         if (do_rope) {
-          const float4* rp = reinterpret_cast<const float4*>(p.rope + pos * 64 + g * 4);
+          const float4* rp = reinterpret_cast<const float4*>(p.rope + (pos + (row < p.seg_rows ? p.rope_off : p.rope_off2)) * 64 + g * 4);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const float4 cs = __ldg(rp + j);     // (cos0, sin0, cos1, sin1)
@@ -293,7 +293,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
               for (int e = 0; e < 8; ++e) x[e] = x[e] * rrms * w[e];
               if (do_rope) {
-                const float4* rp = reinterpret_cast<const float4*>(p.rope + pos * 64 + c * 16 + g * 4);
+                const float4* rp = reinterpret_cast<const float4*>(p.rope + (pos + (row < p.seg_rows ? p.rope_off : p.rope_off2)) * 64 + c * 16 + g * 4);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   const float4 cs = __ldg(rp + j);     // (cos0, sin0, cos1, sin1)
@@ -331,7 +331,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
   } else if (p.mode == EPI_EULER_UNPATCH) {
     // token `row` = (hh, ww) of the patch grid; column n = (c, ph, pw), ps == 2.
     const int Wp = p.Wl / p.ps;
-    const int hh = row / Wp, ww = row - hh * Wp;
+    const int tokg = row + p.tok_off;
+    const int hh = tokg / Wp, ww = tokg - hh * Wp;
     const bool euler = p.sigmas != nullptr;
     float dt = 0.f;
     if (euler) dt = p.sigmas[2 * b + 1] - p.sigmas[2 * b];

@@ -171,3 +171,36 @@ def test_multi_gpu_zimage_fused():
     rel, eng = _zimage_case([f"cuda:{i}" for i in range(n)], 2 * n + 1)
     assert rel < 0.03, rel
     assert any(r.get("fused") for r in eng.metrics.rows), "fused in-process path was not taken"
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("fp8", [False, True])
+def test_batch1_sequence_parallel_ulysses(fp8, monkeypatch):
+    """batch == 1: every GPU of the chain works on the one sample (token-sliced linears, head-sliced attention, peer-pull
+    all-to-all) instead of the reference's sequential layer split; result vs the fp32 oracle, graphs replayed."""
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    n = 2
+    devs = [f"cuda:{i}" for i in range(n)]
+    torch.manual_seed(0)
+    p = flux.FluxParams(in_channels=64, out_channels=64, vec_in_dim=768, context_in_dim=512, hidden_size=512,
+                        mlp_ratio=4.0, num_heads=4, depth=2, depth_single_blocks=2)
+    m = flux.Flux(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    cfg = EngineConfig(fp8=fp8, batch1_mode="ulysses")
+    pa.ParallelAnything().setup_parallel(m, _chain(devs), config=cfg)
+    eng = m._parallel_engine
+    assert eng._ulysses is not None, "sequence-parallel path was not set up"
+    base = flux.example_inputs(p, 1, 256, 256, txt_len=64, device=devs[0], dtype=torch.bfloat16)
+    rels = []
+    with torch.no_grad():
+        for it in range(5):
+            inp = {k: (v * (1.0 - 0.1 * it)).clone() if k == "x" else v.clone() for k, v in base.items()}
+            got = m(inp["x"], inp["timesteps"], context=inp["context"], y=inp["y"], guidance=inp["guidance"])
+            want = oracle(**{k: v.float() for k, v in inp.items()})
+            torch.cuda.synchronize()
+            rels.append((got.float() - want).abs().mean().item() / want.abs().mean().item())
+    eng._ulysses.check_error()
+    assert max(rels) < (0.05 if fp8 else 0.03), rels
+    assert eng.metrics.counters.get("ulysses_steps", 0) == 5
+    assert all(len(s.replica._graphs) >= 1 for s in eng.slots)
+    pa.cleanup_parallel_model(m)
