@@ -667,9 +667,32 @@ class ParallelEngine:
             st = io["slots"][g]
             sp.run_rank(g, wss, xs.data_ptr(), st["t"], st["ctx"], st["y"], st["g"] if ge else None, out.data_ptr())
 
+        caches = [s.replica._graphs for s in self.slots]
+        states = [c.state(gkey) for c in caches]
+        if gkey not in sp.warmed:
+            # very first step of this shape: load every kernel on every GPU without cross-GPU waits (FluxUlysses.warm_up),
+            # one GPU after the other from this thread, then start the real (concurrent) step
+            for g, slot in enumerate(self.slots):
+                st = io["slots"][g]
+                with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
+                    sp.warm_up(g, wss, xs.data_ptr(), st["t"], st["ctx"], st["y"], st["g"] if ge else None, out.data_ptr())
+            for slot in self.slots:
+                torch.cuda.synchronize(slot.device)
+            sp.warmed.add(gkey)
+        if all(st_ == "seen" for st_ in states) and all(c.enabled for c in caches):
+            # second step: capture EVERY GPU's graph before any of them runs.  The step's kernels wait on the other GPUs'
+            # flags, and torch's capture prologue (device synchronise + empty_cache -> cudaFree, which synchronises all
+            # devices) would dead-lock against a peer that already replays its graph (see GraphCache.capture_only).
+            for dsync in self.slots:
+                torch.cuda.synchronize(dsync.device)
+            for g, slot in enumerate(self.slots):
+                with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
+                    caches[g].capture_only(gkey, lambda g=g: body(g))
+            states = [c.state(gkey) for c in caches]
+        all_graph = all(st_ == "graph" for st_ in states)
         launched = False
-        if self._host_exec is not None:
-            handles = [s.replica._graphs.exec_handle(gkey) for s in self.slots]
+        if all_graph and self._host_exec is not None:
+            handles = [c.exec_handle(gkey) for c in caches]
             if all(handles):
                 for s, h in zip(self.slots, handles):
                     self._host_exec.launch_graph(s.index, h, s.stream.cuda_stream)
@@ -684,7 +707,15 @@ class ParallelEngine:
                 pp.set_pipeline_mode(False)
                 faults.check_step(step, slot.name, slot.index)
                 with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
-                    slot.replica._graphs.run(gkey, lambda: body(g))
+                    if all_graph:
+                        caches[g].replay(gkey)
+                    elif states[g] in ("new", "seen") and caches[g].enabled and not all_graph:
+                        # eager pass on every GPU at once (marks the key as seen); mixed states stay eager
+                        body(g)
+                        if caches[g].state(gkey) == "new":
+                            caches[g]._graphs[gkey] = "seen"
+                    else:
+                        body(g)
                     lead_stream.wait_stream(slot.stream)
             futures = [self.slots[g].worker.submit(lambda g=g: run(g)) for g in range(len(self.slots))]
             errors = []

@@ -68,6 +68,8 @@ class FluxUlysses:
         self.err = [torch.zeros(1, dtype=torch.int32, device=d) for d in devs]
         self.flag_tab = [torch.tensor([f.data_ptr() for f in self.flags], dtype=torch.int64, device=d) for d in devs]
         self._ws: Dict[tuple, list] = {}
+        self._dry = False
+        self.warmed = set()
 
     # ------------------------------------------------------------------ geometry / buffers
     def workspace(self, H: int, Wd: int, Lt: int) -> list:
@@ -132,9 +134,20 @@ class FluxUlysses:
     # ------------------------------------------------------------------ one GPU's share of the step
     def _exchange(self, g: int, ws, slot: int, which: str) -> None:
         C = self.C
-        C.sp_signal(self.flag_tab[g], self.n, slot, g, self.epoch[g])
-        C.sp_pull(ws["DESC_" + which], ws["N_" + which], 8 if which == "QKV" else 16, self.flags[g], slot, self.n,
+        peers = 0 if self._dry else self.n        # dry pass: same launches, nobody signals / waits (see run_rank)
+        C.sp_signal(self.flag_tab[g], peers, slot, g, self.epoch[g])
+        C.sp_pull(ws["DESC_" + which], ws["N_" + which], 8 if which == "QKV" else 16, self.flags[g], slot, peers,
                   self.epoch[g], self.timeout_cycles, self.err[g])
+
+    def warm_up(self, g: int, wss, x_ptr: int, t, ctx, y, guidance, out_ptr: int) -> None:
+        """First use on a GPU: run the step's launches ONCE without any cross-GPU wait.  The first launch of a kernel on a
+        device loads its module / sets function attributes, and those driver calls can block on OTHER devices' running
+        kernels - a peer already spinning on this GPU's flag would then dead-lock it until the flag watchdog fires."""
+        self._dry = True
+        try:
+            self.run_rank(g, wss, x_ptr, t, ctx, y, guidance, out_ptr)
+        finally:
+            self._dry = False
 
     def run_rank(self, g: int, wss, x_ptr: int, t, ctx, y, guidance, out_ptr: int) -> int:
         """Everything GPU g does for one step; ``x_ptr`` / ``out_ptr`` are the lead GPU's latent / output buffers
@@ -211,7 +224,8 @@ class FluxUlysses:
                  xout_sample_off=0, x_out_ptr=out_ptr, tok_off=g * Lil)
         # (no closing handshake: the engine orders the lead's staging-buffer rewrite after every GPU's stream, and a GPU
         # cannot run ahead into the next step's first exchange before all peers signalled it)
-        C.sp_epoch_inc(self.epoch[g])
+        if not self._dry:
+            C.sp_epoch_inc(self.epoch[g])
         nl += 3
         return nl
 

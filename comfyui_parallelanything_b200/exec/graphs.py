@@ -56,6 +56,45 @@ class GraphCache:
         except Exception:
             return 0
 
+    def state(self, key) -> str:
+        """'new' | 'seen' (ran eagerly once, next call captures) | 'eager' (capture failed) | 'graph'."""
+        g = self._graphs.get(key)
+        if g is None:
+            return "new"
+        return g if isinstance(g, str) else "graph"
+
+    def capture_only(self, key, body: Callable[[], None]) -> bool:
+        """Capture ``body`` for a key that already ran eagerly once, WITHOUT replaying it.  For step graphs whose kernels
+        wait on other GPUs' flags (sequence-parallel exchanges): torch's capture prologue synchronises the device and
+        empties the caching allocator (``cudaFree`` synchronises every device of the process), so capturing GPU B's graph
+        while GPU A already replays a graph that spins on B's flags dead-locks until the flag watchdog fires.  The
+        engine therefore captures all GPUs' graphs first, from one thread, and only then launches them."""
+        if not self.enabled or self._graphs.get(key) != _SEEN:
+            return self.captured(key) is not None
+        with _CAPTURE_LOCK:
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=self.device)
+            try:
+                with torch.cuda.graph(graph, stream=self._stream, capture_error_mode="thread_local"):
+                    body()
+            except Exception as e:
+                log.warn("CUDA graph capture failed on %s (%s); staying eager for this shape", self.device, e)
+                torch.cuda.synchronize(self.device)
+                self._graphs[key] = _EAGER
+                return False
+        self._graphs[key] = graph
+        self.captures += 1
+        return True
+
+    def replay(self, key) -> None:
+        g = self.captured(key)
+        if g is None:
+            raise KeyError("no captured graph for this key")
+        g.replay()
+        self.replays += 1
+
     def run(self, key, body: Callable[[], None]) -> None:
         if not self.enabled:
             body()
