@@ -136,7 +136,9 @@ class FluxUlysses:
         C = self.C
         peers = 0 if self._dry else self.n        # dry pass: same launches, nobody signals / waits (see run_rank)
         C.sp_signal(self.flag_tab[g], peers, slot, g, self.epoch[g])
-        C.sp_pull(ws["DESC_" + which], ws["N_" + which], 8 if which == "QKV" else 16, self.flags[g], slot, peers,
+        # enough CTAs that ~all SMs hold a few (each thread keeps eight 16-byte peer loads in flight)
+        blocks = max(4, min(64, 592 // ws["N_" + which]))
+        C.sp_pull(ws["DESC_" + which], ws["N_" + which], blocks, self.flags[g], slot, peers,
                   self.epoch[g], self.timeout_cycles, self.err[g])
 
     def warm_up(self, g: int, wss, x_ptr: int, t, ctx, y, guidance, out_ptr: int) -> None:

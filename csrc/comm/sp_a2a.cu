@@ -54,13 +54,32 @@ __global__ void __launch_bounds__(256) sp_pull_kernel(const SpPullDesc* __restri
   const int d = blockIdx.y;
   if (d >= n_desc) return;
   const SpPullDesc ds = descs[d];
-  const int vec_per_row = ds.row_bytes >> 4;
-  const long long total = static_cast<long long>(ds.rows) * vec_per_row;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / vec_per_row), v = static_cast<int>(i - static_cast<long long>(r) * vec_per_row);
-    const int4 val = *reinterpret_cast<const int4*>(ds.src + r * ds.src_pitch + v * 16);
-    *reinterpret_cast<int4*>(ds.dst + r * ds.dst_pitch + v * 16) = val;
+  const int vpr = ds.row_bytes >> 4;                              // 16-byte vectors per row
+  const int total = ds.rows * vpr;
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // eight independent 16-byte peer loads in flight per thread before the first store: a peer load costs ~2 us of NVLink
+  // round trip, so the copy is latency-bound unless every thread keeps several outstanding (first version: 1 -> 384 us
+  // per exchange for 21 MB; the NVLink time of that payload is ~30 us)
+  for (; i + 7 * stride < total; i += 8 * stride) {
+    int4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = i + u * stride;
+      const int r = j / vpr, c = j - r * vpr;
+      v[u] = *reinterpret_cast<const int4*>(ds.src + r * ds.src_pitch + c * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = i + u * stride;
+      const int r = j / vpr, c = j - r * vpr;
+      *reinterpret_cast<int4*>(ds.dst + r * ds.dst_pitch + c * 16) = v[u];
+    }
+  }
+  for (; i < total; i += stride) {
+    const int r = i / vpr, c = i - r * vpr;
+    *reinterpret_cast<int4*>(ds.dst + r * ds.dst_pitch + c * 16) =
+        *reinterpret_cast<const int4*>(ds.src + r * ds.src_pitch + c * 16);
   }
 }
 
