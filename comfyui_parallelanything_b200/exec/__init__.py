@@ -42,6 +42,40 @@ def touch_workspace(cache: dict, key):
     return ws
 
 
+def quantize_block_weights(W: dict, names, tile_of: Callable[[str], int]) -> int:
+    """MXFP8-quantise the block linears ``names`` of a packed weight table in place: ``name.w`` (bf16 [N, K]) becomes
+    ``name.q`` (e4m3 bytes) + ``name.sf`` (UE8M0 scale chunks grouped for the GEMM's B-tile width) + ``name.tile``.
+    Shapes that are not multiples of 128 stay bf16.  Returns the number of quantised matrices."""
+    from .. import ops
+    n = 0
+    for name in names:
+        w = W.get(name + ".w")
+        if w is None or w.shape[0] % 128 or w.shape[1] % 128:
+            continue
+        tile = tile_of(name)
+        W[name + ".q"], W[name + ".sf"] = ops.quantize_mxfp8(W.pop(name + ".w"), tile)
+        W[name + ".tile"] = tile
+        n += 1
+    return n
+
+
+def block_linear(W: dict, a, name: str, mode: str, a8=None, **kw) -> int:
+    """One block Linear of a DiT executor: bf16 tcgen05 GEMM, or - when ``name`` was quantised - MX-quantise the
+    activation (unless the producer already emitted ``a8 = (bytes, scales)``) and run the block-scaled fp8 GEMM; same
+    epilogues either way.  Returns the number of kernel launches."""
+    from .. import ops
+    bias = W.get(name + ".b")
+    if name + ".q" in W:
+        n = 1
+        if a8 is None:
+            a8 = ops.quantize_mxfp8(a)
+            n = 3
+        ops.gemm_fp8(a8[0], a8[1], W[name + ".q"], W[name + ".sf"], mode, W[name + ".tile"], bias=bias, **kw)
+        return n
+    ops.gemm(a, W[name + ".w"], mode, bias=bias, **kw)
+    return 1
+
+
 def builder_for(module: nn.Module) -> Optional[Callable]:
     """Pick the native executor for ``module`` by its STRUCTURE (attribute names + parameter shapes, as ComfyUI's
     own model classes name them - ``exec/recognize.py``), never by ``isinstance`` of this repository's oracle classes:

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from . import cache_workspace, recognize, touch_workspace
+from . import block_linear, cache_workspace, quantize_block_weights, recognize, touch_workspace
 from .graphs import GraphCache
 from ..models import flux as flux_model
 from ..models import wan as wan_model
@@ -83,6 +83,13 @@ class WanExecutor(nn.Module):
         W["head.b"] = _bf(hb_.view(4, oc).permute(1, 0).reshape(4 * oc), d)
         self.W = W
         self.n_blocks = len(model.blocks)
+        # fp8=True: the block GEMMs (qkv / o / cross q / cross o / ffn = ~all of the FLOPs) run as MXFP8 block-scaled
+        # tcgen05 GEMMs (weights quantised once here, activations per GEMM); embedders, text K/V and the head stay bf16
+        self.fp8 = bool(fp8)
+        if self.fp8:
+            names = [f"b{i}.{n_}" for i in range(self.n_blocks) for n_ in ("qkv", "o", "cq", "co", "f0", "f2")]
+            quantize_block_weights(W, names, lambda _n: 224)
+            torch.cuda.empty_cache()
         self.eps = p.eps
         self._ws: Dict[Tuple, dict] = {}
         self._graphs = GraphCache(self.device, enabled=cuda_graphs)
@@ -179,22 +186,22 @@ class WanExecutor(nn.Module):
         for i in range(self.n_blocks):
             # ---- self attention
             ops.layernorm_modulate(X, XM, scale=mod(i, 1), shift=mod(i, 0), eps=self.eps)
-            ops.gemm(XM, W[f"b{i}.qkv.w"], "bias", out=QKV, bias=W[f"b{i}.qkv.b"])
+            block_linear(W, XM, f"b{i}.qkv", "bias", out=QKV)
             C.rms_rope(QKV[:, :, :dim], W[f"b{i}.nq"], ROPE, self.eps)
             C.rms_rope(QKV[:, :, dim:2 * dim], W[f"b{i}.nk"], ROPE, self.eps)
             ops.attention(self._heads(QKV, 0, 3), self._heads(QKV, 1, 3), self._heads(QKV, 2, 3), out=ATT)
-            ops.gemm(ATT, W[f"b{i}.o.w"], "gate_res", out=X, residual=X, gate=mod(i, 2), bias=W[f"b{i}.o.b"])
+            block_linear(W, ATT, f"b{i}.o", "gate_res", out=X, residual=X, gate=mod(i, 2))
             # ---- text cross attention
             ops.layernorm_modulate(X, XM, gamma=W[f"b{i}.n3.g"], beta=W[f"b{i}.n3.b"], eps=self.eps)
-            ops.gemm(XM, W[f"b{i}.cq.w"], "bias", out=ws["CQ"], bias=W[f"b{i}.cq.b"])
+            block_linear(W, XM, f"b{i}.cq", "bias", out=ws["CQ"])
             C.rms_rope(ws["CQ"], W[f"b{i}.cnq"], None, self.eps)
             ops.attention(self._heads(ws["CQ"], 0, 1), self._heads(ws["CKV"][i], 0, 2), self._heads(ws["CKV"][i], 1, 2),
                           out=ATT)
-            ops.gemm(ATT, W[f"b{i}.co.w"], "res", out=X, residual=X, bias=W[f"b{i}.co.b"])
+            block_linear(W, ATT, f"b{i}.co", "res", out=X, residual=X)
             # ---- FFN
             ops.layernorm_modulate(X, XM, scale=mod(i, 4), shift=mod(i, 3), eps=self.eps)
-            ops.gemm(XM, W[f"b{i}.f0.w"], "gelu", out=FF, bias=W[f"b{i}.f0.b"])
-            ops.gemm(FF, W[f"b{i}.f2.w"], "gate_res", out=X, residual=X, gate=mod(i, 5), bias=W[f"b{i}.f2.b"])
+            block_linear(W, XM, f"b{i}.f0", "gelu", out=FF)
+            block_linear(W, FF, f"b{i}.f2", "gate_res", out=X, residual=X, gate=mod(i, 5))
             n += 14
         # ---- head: AdaLN + Linear + unpatchify (+ Euler, + peer store)
         ops.layernorm_modulate(X, XM, scale=ws["HSCALE"][:, 0], shift=ws["HSHIFT"][:, 0], eps=self.eps)

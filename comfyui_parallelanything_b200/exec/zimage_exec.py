@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from . import cache_workspace, recognize, touch_workspace
+from . import block_linear, cache_workspace, quantize_block_weights, recognize, touch_workspace
 from .graphs import GraphCache
 from ..models import flux as flux_model
 from ..models import zimage as zimage_model
@@ -60,11 +60,11 @@ class ZImageExecutor(nn.Module):
 
         def block(name: str, blk):
             a, f = blk.attention, blk.feed_forward
-            W[name + ".qkv"] = _bf(a.qkv.weight, d)
+            W[name + ".qkv.w"] = _bf(a.qkv.weight, d)
             W[name + ".qs"], W[name + ".ks"] = _bf(recognize.norm_scale(a.q_norm), d), _bf(recognize.norm_scale(a.k_norm), d)
-            W[name + ".out"] = _bf(a.out.weight, d)
-            W[name + ".w13"] = ops.interleave_glu(_bf(f.w3.weight, d), _bf(f.w1.weight, d))     # out = w3x * silu(w1x)
-            W[name + ".w2"] = _bf(f.w2.weight, d)
+            W[name + ".out.w"] = _bf(a.out.weight, d)
+            W[name + ".w13.w"] = ops.interleave_glu(_bf(f.w3.weight, d), _bf(f.w1.weight, d))     # out = w3x * silu(w1x)
+            W[name + ".w2.w"] = _bf(f.w2.weight, d)
             for k_, m_ in (("n1", blk.attention_norm1), ("n2", blk.attention_norm2), ("f1", blk.ffn_norm1),
                            ("f2", blk.ffn_norm2)):
                 W[f"{name}.{k_}"] = _bf(m_.weight, d)
@@ -87,6 +87,15 @@ class ZImageExecutor(nn.Module):
         fl = model.final_layer.linear
         W["final.w"] = _bf(fl.weight.view(ps, ps, C, dim).permute(2, 0, 1, 3).reshape(C * ps * ps, dim), d)
         W["final.b"] = _bf(fl.bias.view(ps, ps, C).permute(2, 0, 1).reshape(C * ps * ps), d)
+        self.fp8 = bool(fp8)
+        if self.fp8:
+            # block GEMMs as MXFP8: 256-wide single-accumulator tiles where the epilogue needs whole heads (qkv) or
+            # 64-column [a | g] groups (SwiGLU), double-buffered 224-wide tiles elsewhere
+            blocks = [f"cr{i}" for i in range(len(model.context_refiner))] + \
+                     [f"nr{i}" for i in range(len(model.noise_refiner))] + [f"l{i}" for i in range(len(model.layers))]
+            names = [f"{b}.{n_}" for b in blocks for n_ in ("qkv", "out", "w13", "w2")]
+            quantize_block_weights(W, names, lambda n_: 256 if n_.endswith((".qkv", ".w13")) else 224)
+            torch.cuda.empty_cache()
         self.W = W
         self.n_cr, self.n_nr, self.n_layers = len(model.context_refiner), len(model.noise_refiner), len(model.layers)
         self.eps = p.norm_eps
@@ -146,14 +155,14 @@ class ZImageExecutor(nn.Module):
         sc_m = self._mod(ws, name, 2) if modulated else None
         g_m = self._mod(ws, name, 3) if modulated else None
         ops.rmsnorm_modulate(xs, xms, weight=W[name + ".n1"], scale=sc_a, eps=eps)
-        ops.gemm(xms, W[name + ".qkv"], "qkv_rope", q=q, k=k, v=v, q_scale=W[name + ".qs"], k_scale=W[name + ".ks"],
-                 rope=rope, seq_off=0, qk_eps=eps)
+        block_linear(W, xms, name + ".qkv", "qkv_rope", q=q, k=k, v=v, q_scale=W[name + ".qs"], k_scale=W[name + ".ks"],
+                     rope=rope, seq_off=0, qk_eps=eps)
         ops.attention(q, k, v, out=att)
-        ops.gemm(att, W[name + ".out"], "bias", out=ys)
+        block_linear(W, att, name + ".out", "bias", out=ys)
         ops.rmsnorm_modulate(ys, xs, weight=W[name + ".n2"], gate=g_a, residual=xs, eps=eps)
         ops.rmsnorm_modulate(xs, xms, weight=W[name + ".f1"], scale=sc_m, eps=eps)
-        ops.gemm(xms, W[name + ".w13"], "swiglu", out=ff)
-        ops.gemm(ff, W[name + ".w2"], "bias", out=ys)
+        block_linear(W, xms, name + ".w13", "swiglu", out=ff)
+        block_linear(W, ff, name + ".w2", "bias", out=ys)
         ops.rmsnorm_modulate(ys, xs, weight=W[name + ".f2"], gate=g_m, residual=xs, eps=eps)
         return 9
 

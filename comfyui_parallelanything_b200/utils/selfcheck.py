@@ -1065,3 +1065,32 @@ def groupnorm_cluster_shapes():
     ms = e0.elapsed_time(e1) / 10
     return dict(name="groupnorm_cluster_shapes", ok=bool(ok), mean_rel=res, sdxl_16x16384x320_ms=round(ms, 4),
                 algorithmic_gbs=round(2 * x.numel() * 2 / ms / 1e6, 1))
+
+
+@check
+def wan_zimage_executors_fp8():
+    """WAN and Z-Image executors with MXFP8 block GEMMs (qkv via the drain-first 256-wide tiles for Z-Image, SwiGLU on
+    256-wide tiles, everything else on double-buffered 224-wide tiles) vs the fp32 oracle and vs their bf16 executors."""
+    from ..exec.wan_exec import WanExecutor
+    from ..exec.zimage_exec import ZImageExecutor
+    from ..models import wan, zimage
+    res, ok = {}, True
+    torch.manual_seed(8)
+    wp = wan.wan_tiny_params()
+    zp = zimage.zimage_tiny_params()
+    cases = (("wan", WanExecutor, wan.WanModel, wp, wan.example_inputs(wp, 2, 8, 128, 192, device=_dev(), dtype=torch.bfloat16)),
+             ("zimage", ZImageExecutor, zimage.ZImageModel, zp,
+              zimage.example_inputs(zp, 2, 256, 256, cap_len=32, device=_dev(), dtype=torch.bfloat16)))
+    for name, cls, mcls, params, inp in cases:
+        m = mcls(params).to(device=_dev(), dtype=torch.bfloat16).eval()
+        oracle = mcls(params).to(device=_dev(), dtype=torch.float32).eval()
+        oracle.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+        ex8, ex16 = cls(m, _dev(), fp8=True), cls(m, _dev())
+        with torch.no_grad():
+            got8, got16 = ex8(**inp), ex16(**inp)
+            want = oracle(**{k: v.float() for k, v in inp.items()})
+        r8, r16 = _cmp(name + "_fp8", got8, want, 0.03), _cmp(name + "_bf16", got16, want, 1.0)
+        nq = sum(1 for k in ex8.W if k.endswith(".q"))
+        res[name] = dict(fp8_mean_rel=r8["mean_rel"], bf16_mean_rel=r16["mean_rel"], fp8_max_rel=r8["max_rel"], n_fp8_weights=nq)
+        ok = ok and r8["ok"] and nq > 0 and r8["mean_rel"] <= 3.0 * r16["mean_rel"] + 2e-3
+    return dict(name="wan_zimage_executors_fp8", ok=bool(ok), **res)

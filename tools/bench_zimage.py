@@ -37,6 +37,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="fp8 = MXFP8 block GEMMs in the native executor")
     ap.add_argument("--batch", type=int, default=21)
     ap.add_argument("--cap-len", type=int, default=256)
     a = ap.parse_args()
@@ -69,7 +70,7 @@ def main() -> int:
         torch.manual_seed(1234)
         with torch.device(dev):
             model = zimage.ZImageModel(cfg, dtype=torch.bfloat16).eval()
-        ex = ZImageExecutor(model, dev, cuda_graphs=True)
+        ex = ZImageExecutor(model, dev, cuda_graphs=True, fp8=(a.dtype == "fp8"))
         del model
         torch.cuda.empty_cache()
         if world == 1:
@@ -167,7 +168,7 @@ def main() -> int:
     if rank == 0:
         hb.emit({"metric": hb.METRIC, "value": round(1000.0 / ms, 4), "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
                  "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong",
-                 "vs_baseline": round(1000.0 / ms / PUBLISHED_IT_S, 2), "sec_per_it": round(ms / 1000.0, 4), "dtype": "bf16", "data": "synthetic, random-init weights", "impl": a.impl,
+                 "vs_baseline": round(1000.0 / ms / PUBLISHED_IT_S, 2), "sec_per_it": round(ms / 1000.0, 4), "dtype": (a.dtype if a.impl == "ours" else "bf16"), "data": "synthetic, random-init weights", "impl": a.impl,
                  "clocks": clocks,
                  "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
