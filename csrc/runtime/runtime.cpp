@@ -1,5 +1,7 @@
 #include "runtime.h"
 
+#include "host_executor.h"
+
 #include <ATen/cuda/CUDAContext.h>
 #include <cuda_runtime.h>
 #include <pybind11/stl.h>
@@ -106,92 +108,34 @@ static void memcpy_async(uintptr_t dst, uintptr_t src, size_t bytes, int kind, u
 }
 
 // ------------------------------------------------------------------ HostExecutor
-// One worker thread per device.  Work items are (graph_exec, stream) launches or stream waits; the
-// Python caller enqueues and returns immediately, `sync()` joins all queues (GIL released).
+// One worker thread per device (host_executor.h).  Work items are (graph_exec, stream) launches or stream waits; the
+// Python caller enqueues and returns immediately, `sync()` joins all queues with the GIL released.  This is the launch
+// path of the in-process engine once every replica holds a captured step graph (engine._data_parallel_fused /
+// _forward_ulysses): no Python, no GIL in the per-GPU path.
 class HostExecutor {
  public:
-  explicit HostExecutor(std::vector<int> devices) : devices_(std::move(devices)) {
-    for (size_t i = 0; i < devices_.size(); ++i) {
-      workers_.emplace_back(new Worker());
-      Worker* w = workers_.back().get();
-      int dev = devices_[i];
-      w->thread = std::thread([w, dev] {
-        cudaSetDevice(dev);
-        std::unique_lock<std::mutex> lk(w->mu);
-        for (;;) {
-          w->cv.wait(lk, [w] { return w->stop || !w->q.empty(); });
-          if (w->stop && w->q.empty()) return;
-          auto fn = std::move(w->q.front());
-          w->q.pop();
-          lk.unlock();
-          try {
-            fn();
-          } catch (const std::exception& e) {
-            std::lock_guard<std::mutex> g(w->mu);
-            w->error = e.what();
-          }
-          lk.lock();
-          if (--w->pending == 0) w->done.notify_all();
-        }
-      });
-    }
-  }
-  ~HostExecutor() { shutdown(); }
+  explicit HostExecutor(std::vector<int> devices)
+      : devices_(devices), core_(static_cast<int>(devices.size()), [devices](int slot) { cudaSetDevice(devices[slot]); }) {}
 
   void launch_graph(int slot, uintptr_t graph_exec, uintptr_t stream) {
-    submit(slot, [graph_exec, stream] {
+    core_.submit(slot, [graph_exec, stream] {
       ck(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), reinterpret_cast<cudaStream_t>(stream)),
          "cudaGraphLaunch");
     });
   }
   void stream_sync(int slot, uintptr_t stream) {
-    submit(slot, [stream] { ck(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)), "cudaStreamSynchronize"); });
+    core_.submit(slot, [stream] { ck(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)), "cudaStreamSynchronize"); });
   }
   void sync() {
     py::gil_scoped_release nogil;
-    std::string err;
-    for (auto& w : workers_) {
-      std::unique_lock<std::mutex> lk(w->mu);
-      w->done.wait(lk, [&] { return w->pending == 0; });
-      if (!w->error.empty()) { err = w->error; w->error.clear(); }
-    }
-    if (!err.empty()) throw std::runtime_error(err);
+    core_.sync();
   }
-  void shutdown() {
-    for (auto& w : workers_) {
-      {
-        std::lock_guard<std::mutex> g(w->mu);
-        w->stop = true;
-      }
-      w->cv.notify_all();
-      if (w->thread.joinable()) w->thread.join();
-    }
-    workers_.clear();
-  }
-  int size() const { return (int)devices_.size(); }
+  void shutdown() { core_.shutdown(); }
+  int size() const { return static_cast<int>(devices_.size()); }
 
  private:
-  struct Worker {
-    std::thread thread;
-    std::mutex mu;
-    std::condition_variable cv, done;
-    std::queue<std::function<void()>> q;
-    int pending = 0;
-    bool stop = false;
-    std::string error;
-  };
-  void submit(int slot, std::function<void()> fn) {
-    if (slot < 0 || slot >= (int)workers_.size()) throw std::runtime_error("[pa.rt] bad executor slot");
-    Worker* w = workers_[slot].get();
-    {
-      std::lock_guard<std::mutex> g(w->mu);
-      w->q.push(std::move(fn));
-      ++w->pending;
-    }
-    w->cv.notify_one();
-  }
   std::vector<int> devices_;
-  std::vector<std::unique_ptr<Worker>> workers_;
+  HostExecutorCore core_;
 };
 
 void bind_multicast(py::module_& m);
