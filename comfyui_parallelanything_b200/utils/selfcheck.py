@@ -1094,3 +1094,40 @@ def wan_zimage_executors_fp8():
         res[name] = dict(fp8_mean_rel=r8["mean_rel"], bf16_mean_rel=r16["mean_rel"], fp8_max_rel=r8["max_rel"], n_fp8_weights=nq)
         ok = ok and r8["ok"] and nq > 0 and r8["mean_rel"] <= 3.0 * r16["mean_rel"] + 2e-3
     return dict(name="wan_zimage_executors_fp8", ok=bool(ok), **res)
+
+
+@check
+def cross_attention_cluster_kv():
+    """Small-KV cross-attention kernel (CTA pairs sharing one multicast K/V tile): SDXL shapes (77 keys, head_dim 64,
+    strided q/k/v views of fused projections), a ragged query length and key counts on both sides of the 64-row halves,
+    vs SDPA in fp32; and its time against the general kernel at the SDXL 1024-query shape."""
+    import os
+    res, ok = {}, True
+    for B, H, Lq, Lk in ((2, 20, 1024, 77), (1, 10, 4096, 77), (3, 5, 333, 40), (2, 4, 256, 128), (1, 2, 128, 64)):
+        inner = H * 64
+        qf = _rand(B, Lq, inner, seed=Lq)
+        kvf = _rand(B, Lk, 2 * inner, seed=Lk)
+        q = qf.view(B, Lq, H, 64).permute(0, 2, 1, 3)
+        kv5 = kvf.view(B, Lk, 2, H, 64)
+        k, v = kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3)
+        got = ops.attention(q, k, v, variant=5)
+        want = F.scaled_dot_product_attention(q.float(), k.float(), v.float()).permute(0, 2, 1, 3).reshape(B, Lq, inner)
+        r = _cmp(f"xattn_{B}x{H}x{Lq}x{Lk}", got, want, 0.02)
+        res[f"{B}x{H}x{Lq}x{Lk}"] = round(r["mean_rel"], 5)
+        ok = ok and r["ok"]
+    B, H, Lq, Lk = 16, 20, 1024, 77
+    q = _rand(B, H, Lq, 64)
+    k, v = _rand(B, H, Lk, 64, seed=1), _rand(B, H, Lk, 64, seed=2)
+    out = torch.empty(B, Lq, H * 64, dtype=torch.bfloat16, device=_dev())
+    times = {}
+    for name, variant in (("cluster", 5), ("general", 4)):
+        for _ in range(5):
+            ops.attention(q, k, v, out=out, variant=variant)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.attention(q, k, v, out=out, variant=variant)
+        e1.record()
+        torch.cuda.synchronize()
+        times[name] = round(e0.elapsed_time(e1) / 20 * 1e3, 2)
+    return dict(name="cross_attention_cluster_kv", ok=bool(ok), mean_rel=res, us_sdxl_16x20x1024x77=times)

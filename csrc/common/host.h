@@ -86,6 +86,10 @@ int attention2_bf16(const void* q, const void* k, const void* v, void* out, long
                     int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
                     const long long* v_strides, float scale, cudaStream_t st);
 
+// small-KV cross-attention (Lk <= 128, head_dim 64): a CTA pair shares one multicast K/V tile (csrc/kernels/xattn_cluster.cu)
+int xattn_cluster_bf16(const void* q, const void* k, const void* v, void* out, long long ldo, long long o_bstride, int B,
+                       int H, int Lq, int Lk, int D, const long long* q_strides, const long long* k_strides,
+                       const long long* v_strides, float scale, cudaStream_t st);
 int attention2_fp8out(const void* q, const void* k, const void* v, void* out8, void* sf8, long long ld8, long long rows8,
                       int B, int H, int Lq, int Lk, const long long* qs, const long long* ks, const long long* vs,
                       float scale, cudaStream_t st);

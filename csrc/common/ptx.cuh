@@ -146,6 +146,17 @@ __device__ __forceinline__ void tma_load_4d_s(uint32_t smem_dst, const CUtensorM
       : "memory");
 }
 
+// TMA load multicast to every CTA of the cluster selected by `mask` (same shared-memory offset and the same mbarrier
+// offset in each destination CTA): one CTA fetches the tile from L2 / HBM, all of them receive it.
+__device__ __forceinline__ void tma_load_4d_mcast(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  int c2, int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, "
+      "{%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
