@@ -1102,8 +1102,6 @@ def cross_attention_cluster_kv():
     strided q/k/v views of fused projections), a ragged query length and key counts on both sides of the 64-row halves,
     vs SDPA in fp32; and its time against the general kernel at the SDXL 1024-query shape."""
     import os
-    if os.environ.get("PA_XATTN_CLUSTER", "0") != "1":
-        return dict(name="cross_attention_cluster_kv", ok=True, skipped="opt-in kernel (PA_XATTN_CLUSTER=1)")
     res, ok = {}, True
     for B, H, Lq, Lk in ((2, 20, 1024, 77), (1, 10, 4096, 77), (3, 5, 333, 40), (2, 4, 256, 128), (1, 2, 128, 64)):
         inner = H * 64

@@ -438,7 +438,7 @@ static void attention(Tensor q, Tensor k, Tensor v, Tensor out, double scale, in
           "attention2_debug");
     return;
   }
-  static const bool xattn_cluster = []() { const char* e = std::getenv("PA_XATTN_CLUSTER"); return e && e[0] == '1'; }();
+  static const bool xattn_cluster = []() { const char* e = std::getenv("PA_XATTN_CLUSTER"); return !(e && e[0] == '0'); }();
   if ((xattn_cluster || variant == 5) && D == 64 && k.size(2) <= 128 && (variant == 2 || variant == 5)) {
     // cross-attention over a short conditioning sequence: CTA pairs share one multicast K/V tile
     check(pa::xattn_cluster_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), out.stride(1), out.stride(0),

@@ -179,6 +179,12 @@ xattn_cluster_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
+        if (c * 32 >= Lk) {                                        // chunk entirely past the conditioning length: P = 0
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          ptx::tmem_st_32x32b_x16(s_addr + c * 16, pk);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const float a0 = ex2f(fmaf(__uint_as_float(sv[c * 32 + j]), scale_log2, mneg));
