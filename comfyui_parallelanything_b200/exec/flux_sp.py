@@ -190,6 +190,9 @@ class FluxUlysses:
         def lin(a, name, mode, **kw):
             return ex._lin(a, name, mode, **kw)
 
+        # few heads per GPU: the ping-pong kernel (two 128-row query tiles per CTA) would leave most SMs idle - with fewer
+        # than ~3/4 of a wave, the one-tile-per-CTA kernel doubles the CTA count and halves the attention latency
+        att_variant = 1 if hpg * ((ws["L"] + 255) // 256) < 110 else None
         slot = 0
         for i in range(ex.n_double):
             for s, xs, xms, off, ro in (("img", Xi, XMi, Ltl, ro_i), ("txt", Xt, XMt, 0, ro_t)):
@@ -198,7 +201,7 @@ class FluxUlysses:
                 nl += 1 + lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
                               k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=off, rope_off=ro)
             self._exchange(g, ws, slot, "QKV")                      # all heads / my tokens -> my heads / all tokens
-            ops.attention(ws["QF"], ws["KF"], ws["VF"], out=ws["ATTF"])
+            ops.attention(ws["QF"], ws["KF"], ws["VF"], out=ws["ATTF"], variant=att_variant)
             self._exchange(g, ws, slot + 1, "ATT")                  # my heads / all tokens -> all heads / my tokens
             slot += 2
             nl += 5
@@ -215,7 +218,7 @@ class FluxUlysses:
             nl += 1 + lin(XM, f"s{i}.l1", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"s{i}.qs"], k_scale=W[f"s{i}.ks"],
                           rope=ROPE, seq_off=0, rope_off=ro_t, rope_off2=ro_i, seg_rows=Ltl, out=CAT, mlp_col_off=hid)
             self._exchange(g, ws, slot, "QKV")
-            ops.attention(ws["QF"], ws["KF"], ws["VF"], out=ws["ATTF"])
+            ops.attention(ws["QF"], ws["KF"], ws["VF"], out=ws["ATTF"], variant=att_variant)
             self._exchange(g, ws, slot + 1, "ATT")
             slot += 2
             nl += 5 + lin(CAT, f"s{i}.l2", "gate_res", out=X, residual=X, gate=mod(k, 2))
