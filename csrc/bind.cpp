@@ -118,7 +118,8 @@ static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, int w
   p.mode = mode;
   parse_epilogue(kw, p, /*check_shape=*/true);
   parse_modes(mode, kw, p);
-  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, w_tile, cur_stream()),
+  const int pair = has(kw, "pair") ? kw["pair"].cast<int>() : -1;      // -1 auto | 0 one-CTA kernel | 1 CTA pairs
+  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, w_tile, cur_stream(), pair),
         "gemm_mxfp8");
 }
 

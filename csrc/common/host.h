@@ -22,7 +22,7 @@ int sp_epoch_inc(uint32_t* epoch, cudaStream_t st);
 int num_sms();
 void set_sm_limit(int n);   // per-thread SM budget for persistent-kernel grids (0 = all)
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides = nullptr);
+              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides = nullptr, bool swizzle128 = true);
 int conv_bf16(const void* x, int N, int H, int W, int Cin, const void* w, int taps, int stride, GemmParams p,
               cudaStream_t st);
 
@@ -33,7 +33,7 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
 int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
                         int tile_rows, cudaStream_t st);
 int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
-               cudaStream_t st);
+               cudaStream_t st, int pair = -1);   // pair: -1 auto, 0 one CTA per tile, 1 force the CTA-pair kernel
 
 // out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
 int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,

@@ -351,6 +351,23 @@ __device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t tmem_dst, uint64
   asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
 }
 
+// CTA-pair forms (issued by the leader CTA): the MMA reads both CTAs' shared memory; the copy runs in BOTH CTAs, each
+// from its own shared memory at the descriptor's offset into its own tensor memory.
+__device__ __forceinline__ void mma_mxf8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%5], p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(sfa_tmem), "r"(sfb_tmem), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4_2cta(uint32_t tmem_dst, uint64_t smem_desc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(smem_desc) : "memory");
+}
+
 // All previously issued tcgen05.mma of this thread arrive on `bar` when complete
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {

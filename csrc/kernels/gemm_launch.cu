@@ -28,7 +28,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // rank-N bf16/u8 tensor map with 128-byte swizzle.  dims/strides innermost first; strides[0] is implicit.
 int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides) {
+              const uint32_t* box, int elem_bytes, const uint32_t* elem_strides, bool swizzle128) {
   auto fn = encode_fn();
   if (!fn) return -1;
   cuuint64_t gdim[5], gstr[4];
@@ -39,9 +39,11 @@ int make_tmap(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims,
     es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i];
   }
-  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUtensorMapDataType dt = elem_bytes == 2   ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                           : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                             : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = fn(out, dt, rank, const_cast<void*>(ptr), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[pa] cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u)\n", (int)r, rank,
             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);

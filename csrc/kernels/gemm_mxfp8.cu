@@ -8,6 +8,8 @@
 //   (m0 < 32, m1 < 4) and K-block kb < 4 sits at byte m0*16 + m1*4 + kb.  That is exactly the
 //   32-lane x 128-bit image tcgen05.cp expects: lane m0, 32-bit column m1, byte kb (selected per MMA through
 //   the instruction descriptor's sf_id fields).
+#include <cstdlib>
+
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
@@ -241,6 +243,223 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant
+// A cluster of two CTAs computes one 256 x BN tile (tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale, M = 256).
+// Per 128-byte K block a CTA fills 16 KB of A + BN/2 rows of B (16 KB) instead of 16 + 32 KB: the one-CTA kernel is
+// bound by the L2 -> SM operand stream (ncu: 10.7 TB/s at 56 % tensor pipe), not by the tensor pipe.
+// Scale factors: each CTA keeps the SFA of ITS 128 rows and the SFB of ALL BN columns in its own tensor memory (the
+// tensor core of a CTA scales its 128 x BN accumulator half).  They travel as 512-byte rows of a plain (unswizzled)
+// tensor map so that the peer's loads can complete on the leader's barrier like its A / B tiles do, and one
+// tcgen05.cp.cta_group::2 issued by the leader copies smem -> TMEM in both CTAs.
+template <int BN, int ACC>
+struct Mx8PairCfg {
+  static constexpr int BM = 128, BK = 128;
+  static constexpr int NCHUNK = (BN + 127) / 128;
+  static constexpr int STAGES = 6;
+  static constexpr uint32_t A_BYTES = BM * BK, B_BYTES = (BN / 2) * BK;
+  static constexpr uint32_t SFA_BYTES = 512, SFB_BYTES = 512 * NCHUNK;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SFA_BYTES + SFB_BYTES;
+  static constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t ACC_COLS = ACC * BN;
+  static constexpr uint32_t SF_COL = ACC_COLS;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_STRIDE + 256 + 1024;
+  static_assert(ACC_COLS + 4 + 4 * NCHUNK <= 512, "TMEM budget");
+  static_assert(B_BYTES % 1024 == 0, "B half must be whole 8-row swizzle atoms");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int BN, int ACC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB,
+                       const GemmParams p) {
+  using Cfg = Mx8PairCfg<BN, ACC>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, NCHUNK = Cfg::NCHUNK;
+  constexpr uint32_t SF_OFF = Cfg::A_BYTES + Cfg::B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_STRIDE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t rank = ptx::cluster_ctarank();              // 0: leader (issues copies + MMAs), 1: peer
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmSFA);
+    ptx::prefetch_tmap(&tmSFB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 16);         // eight epilogue warps of each CTA of the pair
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m128_per_batch = (p.rows + BM - 1) / BM;                 // scale-factor chunks are per 128 rows
+  const int m_per_batch = (p.rows + 2 * BM - 1) / (2 * BM);          // 256-row pair tiles per batch entry
+  const int num_m = m_per_batch * p.batch;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+  constexpr int GROUP_M = 4;
+  auto decode = [&](int t, int& mt, int& nt) {
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first = g * GROUP_M;
+    const int gsz = min(num_m - first, GROUP_M);
+    const int r = t - g * per_group;
+    mt = first + r % gsz;
+    nt = r / gsz;
+  };
+
+  if (warp < 4) {
+    if constexpr (ACC == 1) ptx::setmaxnreg_dec<72>();
+    if (warp_u == 0) {
+      // ===================== TMA producer (both CTAs; all bytes land on the leader's `full`) =====================
+      const bool leader_lane = ptx::elect_one();
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int mt, nt;
+        decode(t, mt, nt);
+        const int b = mt / m_per_batch, mp = mt - b * m_per_batch;
+        const int mrow = mp * 2 * BM + static_cast<int>(rank) * BM;
+        const int nrow = nt * BN + static_cast<int>(rank) * (BN / 2);
+        // a pair whose second half lies beyond `rows` still loads (zero-filled) A rows; its scale chunk is clamped
+        // to the last real one (those accumulator rows are never stored)
+        const int m128 = min(mp * 2 + static_cast<int>(rank), m128_per_batch - 1);
+        const int sfa_row = (b * m128_per_batch + m128) * num_k;
+        const int sfb_row = nt * NCHUNK * num_k;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          if (leader_lane) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t sa = smem_u + stage * Cfg::STAGE_STRIDE;
+            ptx::tma_load_3d_2cta(sa, &tmA, &full[stage], kb * BK, mrow, b);
+            ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nrow);
+            ptx::tma_load_2d_2cta(sa + SF_OFF, &tmSFA, &full[stage], 0, sfa_row + kb);
+#pragma unroll
+            for (int j = 0; j < NCHUNK; ++j)
+              ptx::tma_load_2d_2cta(sa + SF_OFF + 512 + j * 512, &tmSFB, &full[stage], 0, sfb_row + j * num_k + kb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else if (warp_u == 1 && rank == 0) {
+      // ===================== scale-factor copies + MMAs (leader CTA only) =====================
+      const bool leader_lane = ptx::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const uint32_t sfa_t = tmem_u + Cfg::SF_COL, sfb_t = tmem_u + Cfg::SF_COL + 4;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int acc = ACC == 2 ? (it & 1) : 0;
+        const uint32_t acc_phase = ACC == 2 ? ((it >> 1) & 1) : (it & 1);
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_u + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          if (leader_lane) {
+            const uint32_t sa = smem_u + stage * Cfg::STAGE_STRIDE;
+            ptx::tmem_cp_32x128b_warpx4_2cta(sfa_t, make_sf_desc(sa + SF_OFF));
+#pragma unroll
+            for (int j = 0; j < NCHUNK; ++j)
+              ptx::tmem_cp_32x128b_warpx4_2cta(sfb_t + 4 * j, make_sf_desc(sa + SF_OFF + 512 + j * 512));
+            const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);
+            const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t idesc = ptx::make_idesc_mxf8(2 * BM, BN, 0, 0, k, k);
+              ptx::mma_mxf8_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, sfa_t, sfb_t, (kb | k) != 0 ? 1u : 0u);
+            }
+            ptx::tc_commit_2cta(&empty[stage], 3);
+            if (kb == num_k - 1) ptx::tc_commit_2cta(&tfull[acc], 3);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    if constexpr (ACC == 1) ptx::setmaxnreg_inc<216>();
+    // eight epilogue warps per CTA: this CTA's 128 rows of the pair's tile, two warps per TMEM lane quadrant
+    constexpr int H0 = BN > 128 ? 128 : 64;
+    constexpr int H1 = BN - H0;
+    const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r_in_tile = q4 * 32 + lane;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      int mt, nt;
+      decode(t, mt, nt);
+      const int b = mt / m_per_batch;
+      const int row = (mt - b * m_per_batch) * 2 * BM + static_cast<int>(rank) * BM + r_in_tile;
+      const int acc = ACC == 2 ? (it & 1) : 0;
+      ptx::mbar_wait(&tfull[acc], ACC == 2 ? ((it >> 1) & 1) : (it & 1));
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + acc * BN;
+      if constexpr (ACC == 1 && BN == 256) {
+        if (p.mode == EPI_QKV_ROPE) {
+          // drain-first (see the one-CTA kernel): registers first, accumulator back to the leader's MMA warp, then math
+          const int ng = nt * BN + half * 128;
+          const bool live = ng < p.N;
+          uint32_t areg[128];
+          if (live) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              ptx::tmem_ld_32x32b_x32(taddr + half * 128 + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&areg[c * 32]));
+            ptx::tmem_ld_wait();
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);
+          if (live) epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          continue;
+        }
+      }
+      if (half == 0)
+        epilogue_tile<H0>(p, taddr, b, row, row < p.rows, nt * BN);
+      else if (nt * BN + H0 < p.N)
+        epilogue_tile<H1>(p, taddr + H0, b, row, row < p.rows, nt * BN + H0);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();                        // nobody leaves (or frees tensor memory) while the pair is still working
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ quantiser
 // bf16 [batch, rows, K] (strided) -> e4m3 [batch, rows, K] + UE8M0 scales in the chunk layout.
 // One thread per 32-element block.  scale = 2^ceil(log2(amax / 448)); rows >= `rows` of the last 128-row
@@ -330,13 +549,71 @@ static int launch_mx8(const CUtensorMap& ta, const CUtensorMap& tb, const void* 
   return (int)cudaGetLastError();
 }
 
+template <int BN, int ACC>
+static int launch_mx8_pair(const void* A, const void* sfa, const void* W, const void* sfb, const GemmParams& p,
+                           cudaStream_t st) {
+  using Cfg = Mx8PairCfg<BN, ACC>;
+  CUtensorMap ta, tb, tsa, tsb;
+  const int num_k = p.K / 128, m128 = (p.rows + 127) / 128, num_n = (p.N + BN - 1) / BN;
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
+    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint32_t box[3] = {128, 128, 1};
+    if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {1, (uint64_t)p.K};
+    uint32_t box[2] = {128, (uint32_t)(BN / 2)};
+    if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
+  }
+  {   // scale chunks as rows of 128 x u32
+    uint64_t dims[2] = {128, (uint64_t)p.batch * m128 * num_k};
+    uint64_t str[2] = {4, 512};
+    uint32_t box[2] = {128, 1};
+    if (make_tmap(&tsa, sfa, 2, dims, str, box, 4, nullptr, false)) return -22;
+    dims[1] = (uint64_t)num_n * Cfg::NCHUNK * num_k;
+    if (make_tmap(&tsb, sfb, 2, dims, str, box, 4, nullptr, false)) return -23;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_2cta_kernel<BN, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  const int tiles = ((p.rows + 255) / 256) * p.batch * num_n;
+  const int max_pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  gemm_mxfp8_2cta_kernel<BN, ACC><<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tsa, tsb, p);
+  return (int)cudaGetLastError();
+}
+
+static bool mx8_pair_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("PA_MXFP8_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 // A: e4m3 [batch, rows, K] contiguous (scales: 128-row tiles), W: e4m3 [N, K] contiguous with scales grouped for
 // `w_tile` = 224 (generic epilogues, double-buffered accumulators), 256 (fused QKV epilogue) or 128.
+// 224- and 256-wide tiles run on CTA pairs (256 x w_tile per pair) when every batch entry has at least 256 rows.
 int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
-               cudaStream_t st) {
+               cudaStream_t st, int pair) {
   if (p.K % 128 || p.N % 32) return -10;
   if (w_tile != 128 && w_tile != 224 && w_tile != 256) return -11;
   if (p.mode == EPI_QKV_ROPE && w_tile == 224) return -12;
+  const bool can_pair = w_tile != 128 && p.rows >= 256;
+  if (pair == 1 && !can_pair) return -13;
+  if (can_pair && (pair == 1 || (pair < 0 && mx8_pair_default()))) {
+    if (w_tile == 224) return launch_mx8_pair<224, 2>(A, sfa, W, sfb, p, st);
+    return launch_mx8_pair<256, 1>(A, sfa, W, sfb, p, st);
+  }
   CUtensorMap ta, tb;
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
