@@ -222,7 +222,12 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
-          if (live) epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          if (live) {
+            if (p.bias != nullptr && p.rope != nullptr)
+              epilogue_qkv_from_regs_fast(p, areg, b, row, row < p.rows, ng);
+            else
+              epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          }
           continue;
         }
       }
@@ -438,7 +443,12 @@ gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);
-          if (live) epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          if (live) {
+            if (p.bias != nullptr && p.rope != nullptr)
+              epilogue_qkv_from_regs_fast(p, areg, b, row, row < p.rows, ng);
+            else
+              epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+          }
           continue;
         }
       }

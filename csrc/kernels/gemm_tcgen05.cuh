@@ -240,6 +240,111 @@ __device__ __forceinline__ void epilogue_qkv_from_regs(const GemmParams& p, cons
   }
 }
 
+// The same epilogue for the common case (bias and RoPE table present), written as straight-line code: no per-group
+// `if (p.bias)` / `if (do_rope)` control flow, so ptxas can hoist the loads, and the per-lane RoPE rows (the only loads
+// that miss L1: 512 B per accumulator row and head) run six column groups ahead of their use.  ncu of the branchy
+// version: the eight epilogue warps were busy for the whole tile period, > 40 % of their samples `long_scoreboard` on the
+// first use of a just-issued load, tensor pipe 65 % (profiles/r2/ncu_mxfp8_l1_ctapair_run31.txt).
+__device__ __forceinline__ void epilogue_qkv_from_regs_fast(const GemmParams& p, uint32_t (&acc)[128], int b, int row,
+                                                            bool row_ok, int ng) {
+  const int qkv_cols = 3 * p.heads * 128;
+  if (ng < qkv_cols) {
+    const int sec = ng / (p.heads * 128);
+    const int head = (ng - sec * p.heads * 128) >> 7;
+    const long long pos = p.seq_off + row;
+    __nv_bfloat16* dst_base = (sec == 0 ? p.q : (sec == 1 ? p.k : p.v));
+    __nv_bfloat16* dst = dst_base + ((static_cast<long long>(b) * p.heads + head) * p.seq_total + pos) * 128;
+    const __nv_bfloat16* bias = p.bias + ng;
+    if (sec == 2) {
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        float x[8], bv[8];
+        ldg8(bias + g * 8, bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[g * 8 + e]) + bv[e];
+        if (row_ok) st8(dst + g * 8, x);
+      }
+      return;
+    }
+    // RoPE row of this accumulator row (rows past the end read row 0 and store nothing)
+    const long long rrow = row_ok ? pos + (row < p.seg_rows ? p.rope_off : p.rope_off2) : 0;
+    const float4* rp = reinterpret_cast<const float4*>(p.rope + rrow * 64);
+    constexpr int RD = 6;                   // column groups of RoPE values in flight per thread
+    float4 rb[RD][2];
+#pragma unroll
+    for (int g = 0; g < RD; ++g) {
+      rb[g][0] = __ldg(rp + 2 * g);
+      rb[g][1] = __ldg(rp + 2 * g + 1);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {          // bias folded into the register copy of the accumulator
+      float bv[8];
+      ldg8(bias + g * 8, bv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float x = __uint_as_float(acc[g * 8 + e]) + bv[e];
+        acc[g * 8 + e] = __float_as_uint(x);
+        ss += x * x;
+      }
+    }
+    const float rrms = rsqrtf(ss * (1.0f / 128.0f) + p.qk_eps);
+    const __nv_bfloat16* nw = sec == 0 ? p.q_scale : p.k_scale;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      const float4 c0 = rb[g % RD][0], c1 = rb[g % RD][1];     // (cos0, sin0, cos1, sin1) x 2
+      if (g + RD < 16) {
+        rb[g % RD][0] = __ldg(rp + 2 * (g + RD));
+        rb[g % RD][1] = __ldg(rp + 2 * (g + RD) + 1);
+      }
+      float w[8], x[8];
+      ldg8(nw + g * 8, w);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(acc[g * 8 + e]) * rrms * w[e];
+      float y[8];
+      y[0] = c0.x * x[0] - c0.y * x[1];
+      y[1] = c0.y * x[0] + c0.x * x[1];
+      y[2] = c0.z * x[2] - c0.w * x[3];
+      y[3] = c0.w * x[2] + c0.z * x[3];
+      y[4] = c1.x * x[4] - c1.y * x[5];
+      y[5] = c1.y * x[4] + c1.x * x[5];
+      y[6] = c1.z * x[6] - c1.w * x[7];
+      y[7] = c1.w * x[6] + c1.z * x[7];
+      if (row_ok) st8(dst + g * 8, y);
+    }
+    return;
+  }
+  if (p.out8 != nullptr) {
+    const long long dcol = p.out8_col_off + (ng - qkv_cols);
+    uint8_t* qrow = p.out8 + b * p.out8_bstride + static_cast<long long>(row) * p.ld8 + dcol;
+    uint32_t sfw = 0;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      float x[32];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float bv[8];
+        ldg8(p.bias + ng + kb * 32 + g * 8, bv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[g * 8 + e] = gelu_tanh(__uint_as_float(acc[kb * 32 + g * 8 + e]) + bv[e]);
+      }
+      sfw |= mx_quant32_store(x, qrow + kb * 32, row_ok) << (8 * kb);
+    }
+    if (row_ok) *reinterpret_cast<uint32_t*>(mx_sf_ptr(p, b, row, dcol)) = sfw;
+    return;
+  }
+  const long long col = p.mlp_col_off + (ng - qkv_cols);
+  __nv_bfloat16* orow = p.out + b * p.out_bstride + static_cast<long long>(row) * p.ldc + col;
+#pragma unroll
+  for (int g = 0; g < 16; ++g) {
+    float x[8], bv[8];
+    ldg8(p.bias + ng + g * 8, bv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = gelu_tanh(__uint_as_float(acc[g * 8 + e]) + bv[e]);
+    if (row_ok) st8(orow + g * 8, x);
+  }
+}
+
 // Fused epilogue of one accumulator tile (thread == accumulator row `row` of batch `b`; `taddr` = this warp's
 // TMEM lane quadrant + accumulator column base; `n0` = first output column of the tile).  Shared by the bf16 and
 // the block-scaled fp8 mainloops.

@@ -93,9 +93,20 @@ elif which == "mxfp8_l1":      # FLUX single-block linear1 (one sample): drain-f
     cat8 = torch.zeros(1, L, hid + mlp, dtype=torch.uint8, device=dev)
     cat8_sf = torch.zeros((L // 128) * ((hid + mlp) // 128) * 512, dtype=torch.uint8, device=dev)
     rope = torch.randn(L, 64, 2, device=dev)
-    for _ in range(4):
+    def l1():
         ops.gemm_fp8(aq, sfa, wq, sfb, "qkv_rope", 256, bias=bias, q=q, k=k, v=v, q_scale=qs, k_scale=ks, rope=rope,
                      seq_off=0, out8=cat8, sf8=cat8_sf, out8_col_off=hid)
+    for _ in range(4):
+        l1()
+    if os.environ.get("PA_TIME"):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(50):
+            l1()
+        ev[1].record()
+        torch.cuda.synchronize()
+        us = ev[0].elapsed_time(ev[1]) / 50 * 1e3
+        print("mxfp8_l1 us/launch", us, "TFLOP/s", 2.0 * L * (3 * hid + mlp) * hid / us / 1e6)
 elif which == "scatter_conv":
     C_ = ops.require()
     x = torch.randn(2, 4, 128, 128, **bf)
