@@ -85,7 +85,7 @@ class ParallelEngine:
         self._native_shells: List[Any] = []    # executors of the same geometry on other GPUs, filled over NVLink
         self.setup_report: Dict[str, Any] = {}
         self._host_exec = None                 # native per-GPU launcher threads (csrc/runtime HostExecutor)
-        self._ulysses = None                   # sequence-parallel batch-1 path (exec/flux_sp.py), native FLUX replicas only
+        self._ulysses = None                   # sequence-parallel batch-1 path (exec/{flux,wan}_sp.py), native replicas only
         self.active = False
 
     # ------------------------------------------------------------------ setup
@@ -226,15 +226,15 @@ class ParallelEngine:
             ok = False
         self._peer_ready = bool(ok) and len(native) == len(self.slots)
         if self._peer_ready and self.config.batch1_mode in ("auto", "ulysses") and self.config.workload_split:
-            from .exec import flux_sp
-            why = flux_sp.supported([s.replica for s in self.slots])
-            if why is None:
-                try:
-                    self._ulysses = flux_sp.FluxUlysses([s.replica for s in self.slots],
-                                                        timeout_ms=self.config.flag_timeout_ms)
-                    log.info("batch=1 will run sequence-parallel (Ulysses) over %d GPUs", len(self.slots))
-                except Exception as e:
-                    log.warn("sequence-parallel batch=1 path unavailable: %s", e)
+            from .exec import sp_common
+            try:
+                self._ulysses, why = sp_common.build([s.replica for s in self.slots],
+                                                     timeout_ms=self.config.flag_timeout_ms)
+            except Exception as e:
+                self._ulysses, why = None, str(e)
+            if self._ulysses is not None:
+                log.info("batch=1 will run sequence-parallel (Ulysses, %s) over %d GPUs", self._ulysses.family,
+                         len(self.slots))
             elif self.config.batch1_mode == "ulysses":
                 log.warn("PA_BATCH1=ulysses requested but %s; using the layer-split mode", why)
         if self._peer_ready and self.config.host_threads and self.config.cuda_graphs:
@@ -608,64 +608,44 @@ class ParallelEngine:
         res = out.clone()
         return res if x.dtype == res.dtype else res.to(x.dtype)
 
-    # ---- batch == 1: sequence-parallel (Ulysses) over all native FLUX replicas --------------------------------------
+    # ---- batch == 1: sequence-parallel (Ulysses) over all native FLUX / WAN replicas -------------------------------
     def _can_ulysses(self, x, timesteps, context) -> bool:
         if not (isinstance(x, torch.Tensor) and isinstance(context, torch.Tensor) and isinstance(timesteps, torch.Tensor)):
             return False
-        if x.device != self.lead_device or x.dim() != 4 or not x.is_floating_point():
+        if x.device != self.lead_device or not x.is_floating_point():
             return False
-        n = len(self.slots)
-        H, Wd, Lt = x.shape[2], x.shape[3], context.shape[1]
-        return H % 2 == 0 and Wd % 2 == 0 and Lt % n == 0 and ((H // 2) * (Wd // 2)) % n == 0 and Lt >= n
+        return bool(self._ulysses.accepts(x, context))
 
     def _forward_ulysses(self, step, x, timesteps, context, kwargs):
         """One sample, every GPU of the chain: token-sliced linear layers, head-sliced attention, peer-pull all-to-all
-        (exec/flux_sp.py).  Inputs are staged into fixed buffers (a sampler passes fresh tensors), each GPU's share of
+        (exec/flux_sp.py, exec/wan_sp.py).  Inputs are staged into fixed buffers (a sampler passes fresh tensors), each GPU's share of
         the step is one CUDA graph; the velocity rows land in the lead GPU's output buffer through the fused gather."""
         sp = self._ulysses
         lead_dev = self.lead_device
         lead_stream = torch.cuda.current_stream(lead_dev)
-        y, guidance = kwargs.get("y"), kwargs.get("guidance")
         bf = torch.bfloat16
-        key = ("sp", tuple(x.shape), tuple(context.shape), None if y is None else tuple(y.shape), guidance is not None)
+        key = sp.io_key(x, context, kwargs)
         io = self._io.get(key)
         if io is None:
             io = {"x": torch.empty(tuple(x.shape), dtype=bf, device=lead_dev),
-                  "out": torch.empty(tuple(x.shape), dtype=bf, device=lead_dev), "slots": []}
-            ex0 = self.slots[0].replica
-            for slot in self.slots:
-                d = slot.device
-                io["slots"].append({
-                    "t": torch.empty(1, dtype=bf, device=d), "ctx": torch.empty(tuple(context.shape), dtype=bf, device=d),
-                    "y": torch.zeros(1, ex0.params.vec_in_dim, dtype=bf, device=d),
-                    "g": torch.ones(1, dtype=bf, device=d), "ctx_src": None})
+                  "out": torch.empty(tuple(x.shape), dtype=bf, device=lead_dev),
+                  "slots": [sp.slot_buffers(slot.device, x, context, kwargs) for slot in self.slots]}
             if len(self._io) >= 8:
                 self._io.pop(next(iter(self._io)))
             self._io[key] = io
         t0 = time.perf_counter()
         xs, out = io["x"], io["out"]
         xs.copy_(x, non_blocking=True)
-        wss = sp.workspace(x.shape[2], x.shape[3], context.shape[1])
-        for slot, st in zip(self.slots, io["slots"]):
-            with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream):
+        wss = sp.workspace(*sp.geometry(x, context))
+        for g, (slot, st) in enumerate(zip(self.slots, io["slots"])):
+            with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
                 slot.stream.wait_stream(lead_stream)
-                st["t"].copy_(timesteps.reshape(-1)[:1], non_blocking=True)
-                ident = (id(context), context.data_ptr(), context._version)
-                if not self.config.cache_conditioning or st["ctx_src"] is None or st["ctx_src"][0] != ident:
-                    st["ctx"].copy_(context, non_blocking=True)
-                    st["ctx_src"] = (ident, context)
-                if y is not None:
-                    st["y"].copy_(y[:, :st["y"].shape[1]], non_blocking=True)
-                if guidance is not None:
-                    st["g"].copy_(guidance.reshape(-1)[:1], non_blocking=True)
-        ge = self.slots[0].replica.params.guidance_embed
-        if ge and guidance is None:
-            raise ValueError("guidance-distilled model needs a guidance strength")
+                sp.stage(st, timesteps, context, kwargs, self.config.cache_conditioning)
+                sp.pre_step(g, wss, st)          # conditioning-only precomputes stay outside the step graph
         gkey = ("sp",) + key[1:]
 
         def body(g):
-            st = io["slots"][g]
-            sp.run_rank(g, wss, xs.data_ptr(), st["t"], st["ctx"], st["y"], st["g"] if ge else None, out.data_ptr())
+            sp.run_rank(g, wss, xs.data_ptr(), io["slots"][g], out.data_ptr())
 
         caches = [s.replica._graphs for s in self.slots]
         states = [c.state(gkey) for c in caches]
@@ -673,9 +653,8 @@ class ParallelEngine:
             # very first step of this shape: load every kernel on every GPU without cross-GPU waits (FluxUlysses.warm_up),
             # one GPU after the other from this thread, then start the real (concurrent) step
             for g, slot in enumerate(self.slots):
-                st = io["slots"][g]
                 with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream), torch.no_grad():
-                    sp.warm_up(g, wss, xs.data_ptr(), st["t"], st["ctx"], st["y"], st["g"] if ge else None, out.data_ptr())
+                    sp.warm_up(g, wss, xs.data_ptr(), io["slots"][g], out.data_ptr())
             for slot in self.slots:
                 torch.cuda.synchronize(slot.device)
             sp.warmed.add(gkey)

@@ -113,6 +113,10 @@ class FluxExecutor(nn.Module):
         if self.fp8:
             big = [k[:-2] for k in list(W) if k.endswith(".w") and (k.startswith("d") or k.startswith("s"))
                    and k.split(".")[-2] in ("qkv", "proj", "mlp0", "mlp2", "l1", "l2")]
+            # the modulation table (all blocks' adaLN linears, 1 056 768 x 3072 for FLUX.1-dev) is a pure weight stream
+            # (6.5 GB in bf16 for <= 8 rows of activations): as MXFP8 it is half the bytes
+            if os.environ.get("PA_FP8_MOD", "1") != "0":
+                big.append("mod")
             for name in big:
                 w = W.pop(name + ".w")
                 if w.shape[0] % 128 or w.shape[1] % 128:
@@ -245,8 +249,7 @@ class FluxExecutor(nn.Module):
             n += 1
         ops.gemm(y, W["vector_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["vector_in.in.b"])
         ops.gemm(HC, W["vec_out.w"], "silu", out=ws["SVEC"], bias=W["vec_out.b"])          # silu(vec)
-        ops.gemm(ws["SVEC"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])            # all modulations
-        n += 3
+        n += 2 + self._lin(ws["SVEC"], "mod", "bias", out=ws["MOD"])                         # all modulations
         # ---- double-stream blocks
         # Between two joint attentions the txt and img chains are independent.  Run back to back, the 512-row txt
         # GEMMs fill 24-96 of the 74 CTA-pair slots and the img GEMMs end in a partial wave; forked onto two streams

@@ -18,14 +18,13 @@ NVLink time per step next to ~6 ms of compute.
 """
 from __future__ import annotations
 
-import struct
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 
 from .. import ops
 from ..models import flux as flux_model
-from ..utils import log
+from .sp_common import UlyssesBase
 
 
 def supported(executors) -> Optional[str]:
@@ -46,30 +45,48 @@ def supported(executors) -> Optional[str]:
     return None
 
 
-class FluxUlysses:
+class FluxUlysses(UlyssesBase):
     """Wires N FluxExecutors (one per GPU, same process) for sequence-parallel batch-1 steps."""
+    family = "flux"
 
     def __init__(self, executors: List, timeout_ms: int = 20000):
         why = supported(executors)
         if why:
             raise ValueError(f"sequence-parallel FLUX unavailable: {why}")
-        self.ex = list(executors)
-        self.n = len(executors)
-        self.C = ops.require()
-        C = self.C
-        devs = [e.device for e in self.ex]
-        for a in devs:
-            for b in devs:
-                if a != b and not C.enable_peer_access(a.index, b.index):
-                    raise RuntimeError(f"no peer access {a} -> {b}")
-        self.timeout_cycles = int(timeout_ms * 1.9e6)
-        self.flags = [torch.zeros(C.SP_MAX_SLOTS * C.SP_MAX_RANKS, dtype=torch.int32, device=d) for d in devs]
-        self.epoch = [torch.ones(1, dtype=torch.int32, device=d) for d in devs]
-        self.err = [torch.zeros(1, dtype=torch.int32, device=d) for d in devs]
-        self.flag_tab = [torch.tensor([f.data_ptr() for f in self.flags], dtype=torch.int64, device=d) for d in devs]
-        self._ws: Dict[tuple, list] = {}
-        self._dry = False
-        self.warmed = set()
+        super().__init__(executors, timeout_ms)
+
+    # ------------------------------------------------------------------ engine-facing protocol
+    def accepts(self, x, context) -> bool:
+        if x.dim() != 4 or context.dim() != 3:
+            return False
+        n = self.n
+        H, Wd, Lt = x.shape[2], x.shape[3], context.shape[1]
+        return H % 2 == 0 and Wd % 2 == 0 and Lt % n == 0 and ((H // 2) * (Wd // 2)) % n == 0 and Lt >= n
+
+    def geometry(self, x, context) -> tuple:
+        return (x.shape[2], x.shape[3], context.shape[1])
+
+    def io_key(self, x, context, kwargs) -> tuple:
+        y = kwargs.get("y")
+        return ("sp", tuple(x.shape), tuple(context.shape), None if y is None else tuple(y.shape),
+                kwargs.get("guidance") is not None)
+
+    def slot_buffers(self, device, x, context, kwargs) -> dict:
+        st = super().slot_buffers(device, x, context, kwargs)
+        bf = torch.bfloat16
+        st["y"] = torch.zeros(1, self.ex[0].params.vec_in_dim, dtype=bf, device=device)
+        st["g"] = torch.ones(1, dtype=bf, device=device)
+        return st
+
+    def stage(self, st, timesteps, context, kwargs, cache_conditioning: bool) -> None:
+        super().stage(st, timesteps, context, kwargs, cache_conditioning)
+        y, guidance = kwargs.get("y"), kwargs.get("guidance")
+        if y is not None:
+            st["y"].copy_(y[:, :st["y"].shape[1]], non_blocking=True)
+        if guidance is not None:
+            st["g"].copy_(guidance.reshape(-1)[:1], non_blocking=True)
+        elif self.ex[0].params.guidance_embed:
+            raise ValueError("guidance-distilled model needs a guidance strength")
 
     # ------------------------------------------------------------------ geometry / buffers
     def workspace(self, H: int, Wd: int, Lt: int) -> list:
@@ -126,35 +143,13 @@ class FluxUlysses:
         self._ws[key] = wss
         return wss
 
-    def _table(self, rows, device) -> torch.Tensor:
-        blob = b"".join(struct.pack("<QQqqii", s, d, sp, dp, r, rb) for s, d, sp, dp, r, rb in rows)
-        assert len(blob) == len(rows) * self.C.SP_DESC_BYTES
-        return torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
-
     # ------------------------------------------------------------------ one GPU's share of the step
-    def _exchange(self, g: int, ws, slot: int, which: str) -> None:
-        C = self.C
-        peers = 0 if self._dry else self.n        # dry pass: same launches, nobody signals / waits (see run_rank)
-        C.sp_signal(self.flag_tab[g], peers, slot, g, self.epoch[g])
-        # enough CTAs that ~all SMs hold a few (each thread keeps eight 16-byte peer loads in flight)
-        blocks = max(4, min(64, 592 // ws["N_" + which]))
-        C.sp_pull(ws["DESC_" + which], ws["N_" + which], blocks, self.flags[g], slot, peers,
-                  self.epoch[g], self.timeout_cycles, self.err[g])
-
-    def warm_up(self, g: int, wss, x_ptr: int, t, ctx, y, guidance, out_ptr: int) -> None:
-        """First use on a GPU: run the step's launches ONCE without any cross-GPU wait.  The first launch of a kernel on a
-        device loads its module / sets function attributes, and those driver calls can block on OTHER devices' running
-        kernels - a peer already spinning on this GPU's flag would then dead-lock it until the flag watchdog fires."""
-        self._dry = True
-        try:
-            self.run_rank(g, wss, x_ptr, t, ctx, y, guidance, out_ptr)
-        finally:
-            self._dry = False
-
-    def run_rank(self, g: int, wss, x_ptr: int, t, ctx, y, guidance, out_ptr: int) -> int:
+    def run_rank(self, g: int, wss, x_ptr: int, st: dict, out_ptr: int) -> int:
         """Everything GPU g does for one step; ``x_ptr`` / ``out_ptr`` are the lead GPU's latent / output buffers
-        (peer mappings), ``t / ctx / y / guidance`` device-resident on GPU g.  Returns the launch count."""
+        (peer mappings), ``st`` the step inputs staged on GPU g (t / ctx / y / guidance).  Returns the launch count."""
         ex, ws, C = self.ex[g], wss[g], self.C
+        t, ctx, y = st["t"], st["ctx"], st["y"]
+        guidance = st["g"] if ex.params.guidance_embed else None
         W, hid, mlp, n = ex.W, ex.hid, ex.mlp, self.n
         Lt, Li, Ltl, Lil, Ll, hpg = ws["Lt"], ws["Li"], ws["Ltl"], ws["Lil"], ws["Ll"], ws["hpg"]
         X, XM, CAT, Q, K, V, ROPE = ws["X"], ws["XM"], ws["CAT"], ws["Q"], ws["K"], ws["V"], ws["ROPE"]
@@ -180,8 +175,7 @@ class FluxUlysses:
             nl += 2
         ops.gemm(y, W["vector_in.in.w"], "silu", out=HC[:, col:col + hid], bias=W["vector_in.in.b"])
         ops.gemm(HC, W["vec_out.w"], "silu", out=ws["SVEC"], bias=W["vec_out.b"])
-        ops.gemm(ws["SVEC"], W["mod.w"], "bias", out=ws["MOD"], bias=W["mod.b"])
-        nl += 3
+        nl += 2 + ex._lin(ws["SVEC"], "mod", "bias", out=ws["MOD"])
 
         def mod(key, idx):
             off = ex.mod_off[key] + idx * hid
@@ -229,16 +223,6 @@ class FluxUlysses:
                  xout_sample_off=0, x_out_ptr=out_ptr, tok_off=g * Lil)
         # (no closing handshake: the engine orders the lead's staging-buffer rewrite after every GPU's stream, and a GPU
         # cannot run ahead into the next step's first exchange before all peers signalled it)
-        if not self._dry:
-            C.sp_epoch_inc(self.epoch[g])
+        self._end_step(g)
         nl += 3
         return nl
-
-    def check_error(self) -> None:
-        for g, e in enumerate(self.err):
-            v = int(e.item()) & 0xFFFFFFFF
-            if v:
-                raise RuntimeError(f"sequence-parallel exchange timed out on GPU {g}: 0x{v:08x} (dead or stalled peer)")
-
-    def release(self) -> None:
-        self._ws.clear()

@@ -204,3 +204,37 @@ def test_batch1_sequence_parallel_ulysses(fp8, monkeypatch):
     assert eng.metrics.counters.get("ulysses_steps", 0) == 5
     assert all(len(s.replica._graphs) >= 1 for s in eng.slots)
     pa.cleanup_parallel_model(m)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("fp8", [False, True])
+def test_batch1_sequence_parallel_ulysses_wan(fp8):
+    """The video family at batch 1 (its usual workload): token-sliced linears + q/k norm + RoPE, head-sliced
+    self-attention between two peer-pull exchanges, local text cross-attention; result vs the fp32 oracle, a new latent
+    tensor every step, graphs replayed from the third step on."""
+    from comfyui_parallelanything_b200.models import wan
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    n = 2
+    devs = [f"cuda:{i}" for i in range(n)]
+    torch.manual_seed(0)
+    p = wan.wan_tiny_params()
+    m = wan.WanModel(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    cfg = EngineConfig(fp8=fp8, batch1_mode="ulysses")
+    pa.ParallelAnything().setup_parallel(m, _chain(devs), config=cfg)
+    eng = m._parallel_engine
+    assert eng._ulysses is not None and eng._ulysses.family == "wan", "sequence-parallel WAN path was not set up"
+    base = wan.example_inputs(p, 1, frames=8, height=64, width=64, device=devs[0], dtype=torch.bfloat16)
+    rels = []
+    with torch.no_grad():
+        for it in range(5):
+            inp = {k: (v * (1.0 - 0.1 * it)).clone() if k == "x" else v.clone() for k, v in base.items()}
+            got = m(inp["x"], inp["timesteps"], context=inp["context"])
+            want = oracle(**{k: v.float() for k, v in inp.items()})
+            torch.cuda.synchronize()
+            rels.append((got.float() - want).abs().mean().item() / want.abs().mean().item())
+    eng._ulysses.check_error()
+    assert max(rels) < (0.05 if fp8 else 0.03), rels
+    assert eng.metrics.counters.get("ulysses_steps", 0) == 5
+    assert all(len(s.replica._graphs) >= 1 for s in eng.slots)
+    pa.cleanup_parallel_model(m)
