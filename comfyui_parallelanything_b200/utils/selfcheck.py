@@ -743,7 +743,8 @@ def gemm_mxfp8():
         wq, sfb = ops.quantize_mxfp8(w, tile)
         wd = ops.dequantize_mxfp8(wq, sfb, tile)[0]
         exact = F.gelu(ad @ wd.t() + bias.float(), approximate="tanh")
-        for pair in ((0,) if tile == 128 else (0, 1)):       # one CTA per tile | CTA pairs (256-row tiles, ragged M)
+        # one CTA per tile | CTA pairs (256-row tiles, ragged M) | CTA pairs with split-N accumulators (256-wide only)
+        for pair in ((0,) if tile == 128 else ((0, 1) if tile == 224 else (0, 1, 2))):
             out = torch.zeros(B, M, N, dtype=torch.bfloat16, device=_dev())
             ops.gemm_fp8(aq, sfa, wq, sfb, "gelu", tile, out=out, bias=bias, pair=pair)
             r = _cmp(f"gemm_mxfp8_t{tile}_pair{pair}", out, exact, 0.01)
@@ -764,7 +765,7 @@ def gemm_mxfp8_flux_shape():
     res = {}
     r = None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for tile, pair in ((224, 0), (224, 1), (256, 0), (256, 1), (128, 0)):
+    for tile, pair in ((224, 0), (224, 1), (256, 0), (256, 1), (256, 2), (128, 0)):
         wq, sfb = ops.quantize_mxfp8(w, tile)
         out = torch.empty(M, N, dtype=torch.bfloat16, device=_dev())
         ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
@@ -781,7 +782,7 @@ def gemm_mxfp8_flux_shape():
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        res[f"tile{tile}{'_pair' if pair else ''}_tflops"] = round(2.0 * M * N * K / ms / 1e9, 1)
+        res[f"tile{tile}{('', '_pair', '_pairsplit')[pair]}_tflops"] = round(2.0 * M * N * K / ms / 1e9, 1)
     o16 = torch.empty(M, N, dtype=torch.bfloat16, device=_dev())
     for _ in range(3):
         ops.gemm(a, w, "bias", out=o16)

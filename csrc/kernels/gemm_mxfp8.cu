@@ -470,6 +470,261 @@ gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------ CTA pairs, split-N accumulators (256-wide tiles)
+// The 256 x 256 pair tile above has ONE accumulator (2 x 256 columns + scale factors do not fit the 512 TMEM columns), and
+// tensor memory drains at 64 B/clk: 128 KB per CTA = 2 048 cycles per tile during which the tensor pipe idles (ncu: 72 %
+// active vs 86 % for the double-buffered 224-wide tiles).  Here the tile is two 128-column halves in THREE rotating
+// 128-column accumulators (384 + 6 x 12 scale-factor columns).  Per K block the leader issues the half-0 MMAs (N = 128) and
+// the half-1 MMAs separately; half 0 runs LAG K blocks ahead at the start of a tile and finishes LAG K blocks early at
+// its end:
+//     h0[0..LAG) | wait buffer of h1 | h1[0..LAG) | (h0[k] h1[k]) ... | h0[last LAG] -> commit | h1[last LAG] -> commit
+// The next tile's half 0 starts at once in the spare buffer; its half 1 needs the buffer that this tile's half 0 handed
+// to the epilogue 2 x LAG x 256 tensor cycles earlier - more than the ~1 000 cycles its drain takes.  Scale factors are
+// kept per pipeline stage in tensor memory (a stage is touched by half 0 first and by half 1 up to LAG K blocks later).
+struct Mx8SplitCfg {
+  static constexpr int BM = 128, BN = 256, BK = 128, HN = 128;
+  static constexpr int STAGES = 6, LAG = 3, NACC = 3;
+  static constexpr uint32_t A_BYTES = BM * BK, BH_BYTES = (HN / 2) * BK;          // this CTA's 64 rows of one B half
+  static constexpr uint32_t B_BYTES = 2 * BH_BYTES;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + 512 + 1024;
+  static constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr uint32_t SF_COL = NACC * HN;                                   // 12 columns per stage from here
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_STRIDE + 256 + 1024;
+  static_assert(SF_COL + 12 * STAGES <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_mxfp8_2cta_split_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const __grid_constant__ CUtensorMap tmSFA, const __grid_constant__ CUtensorMap tmSFB,
+                             const GemmParams p) {
+  using Cfg = Mx8SplitCfg;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, HN = Cfg::HN, STAGES = Cfg::STAGES, LAG = Cfg::LAG;
+  constexpr uint32_t SF_OFF = Cfg::A_BYTES + Cfg::B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_STRIDE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;          // 3
+  uint64_t* tempty = tfull + 3;              // 3
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 3);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmSFA);
+    ptx::prefetch_tmap(&tmSFB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 3; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 8);          // four epilogue warps (one per lane quadrant) of each CTA drain a half
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 2) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m128_per_batch = (p.rows + BM - 1) / BM;
+  const int m_per_batch = (p.rows + 2 * BM - 1) / (2 * BM);
+  const int num_m = m_per_batch * p.batch;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_k = p.K / BK;
+  constexpr int GROUP_M = 4;
+  auto decode = [&](int t, int& mt, int& nt) {
+    const int per_group = GROUP_M * num_n;
+    const int g = t / per_group;
+    const int first = g * GROUP_M;
+    const int gsz = min(num_m - first, GROUP_M);
+    const int r = t - g * per_group;
+    mt = first + r % gsz;
+    nt = r / gsz;
+  };
+
+  if (warp < 4) {
+    ptx::setmaxnreg_dec<72>();
+    if (warp_u == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      const bool leader_lane = ptx::elect_one();
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        int mt, nt;
+        decode(t, mt, nt);
+        const int b = mt / m_per_batch, mp = mt - b * m_per_batch;
+        const int mrow = mp * 2 * BM + static_cast<int>(rank) * BM;
+        const int nrow = nt * BN + static_cast<int>(rank) * (HN / 2);       // + h * 128 for half h
+        const int m128 = min(mp * 2 + static_cast<int>(rank), m128_per_batch - 1);
+        const int sfa_row = (b * m128_per_batch + m128) * num_k;
+        const int sfb_row = nt * 2 * num_k;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          if (leader_lane) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+            const uint32_t sa = smem_u + stage * Cfg::STAGE_STRIDE;
+            ptx::tma_load_3d_2cta(sa, &tmA, &full[stage], kb * BK, mrow, b);
+            ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES, &tmB, &full[stage], kb * BK, nrow);
+            ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES + Cfg::BH_BYTES, &tmB, &full[stage], kb * BK, nrow + HN);
+            ptx::tma_load_2d_2cta(sa + SF_OFF, &tmSFA, &full[stage], 0, sfa_row + kb);
+            ptx::tma_load_2d_2cta(sa + SF_OFF + 512, &tmSFB, &full[stage], 0, sfb_row + kb);
+            ptx::tma_load_2d_2cta(sa + SF_OFF + 1024, &tmSFB, &full[stage], 0, sfb_row + num_k + kb);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else if (warp_u == 1 && rank == 0) {
+      // ===================== scale-factor copies + MMAs (leader CTA only) =====================
+      const bool leader_lane = ptx::elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t smem_u = __shfl_sync(0xffffffffu, ptx::smem_u32(smem), 0);
+      int s0 = 0, s1 = 0;                     // pipeline stage cursors of half 0 (waits for the loads) and half 1 (releases)
+      uint32_t ph0 = 0;
+      const bool lagged = num_k >= 2 * LAG;
+      // (macros, not lambdas: by-reference captures put the stage cursors into local memory)
+      // half 0 of K block kb: first touch of the stage -> wait for its loads, copy its scale factors to TMEM
+#define PA_MX8_H0(kb, d_tmem)                                                                                              \
+  do {                                                                                                                     \
+    ptx::mbar_wait(&full[s0], ph0);                                                                                        \
+    ptx::tc_fence_after();                                                                                                 \
+    if (leader_lane) {                                                                                                     \
+      const uint32_t sa = smem_u + s0 * Cfg::STAGE_STRIDE;                                                                 \
+      const uint32_t sf_t = tmem_u + Cfg::SF_COL + 12 * s0;                                                                \
+      ptx::tmem_cp_32x128b_warpx4_2cta(sf_t, make_sf_desc(sa + SF_OFF));                                                   \
+      ptx::tmem_cp_32x128b_warpx4_2cta(sf_t + 4, make_sf_desc(sa + SF_OFF + 512));                                         \
+      ptx::tmem_cp_32x128b_warpx4_2cta(sf_t + 8, make_sf_desc(sa + SF_OFF + 1024));                                        \
+      const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);                                                              \
+      const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES);                                               \
+      _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                                        \
+          ptx::mma_mxf8_ss_2cta((d_tmem), adesc + 2 * k, bdesc + 2 * k, ptx::make_idesc_mxf8(2 * BM, HN, 0, 0, k, k), sf_t, \
+                                sf_t + 4, ((kb) | k) != 0 ? 1u : 0u);                                                      \
+    }                                                                                                                      \
+    if (++s0 == STAGES) {                                                                                                  \
+      s0 = 0;                                                                                                              \
+      ph0 ^= 1;                                                                                                            \
+    }                                                                                                                      \
+  } while (0)
+      // half 1 of K block kb: the stage is resident and its scale factors sit in TMEM; release the stage afterwards
+#define PA_MX8_H1(kb, d_tmem)                                                                                              \
+  do {                                                                                                                     \
+    if (leader_lane) {                                                                                                     \
+      const uint32_t sa = smem_u + s1 * Cfg::STAGE_STRIDE;                                                                 \
+      const uint32_t sf_t = tmem_u + Cfg::SF_COL + 12 * s1;                                                                \
+      const uint64_t adesc = ptx::make_desc_kmajor_sw128(sa);                                                              \
+      const uint64_t bdesc = ptx::make_desc_kmajor_sw128(sa + Cfg::A_BYTES + Cfg::BH_BYTES);                               \
+      _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                                        \
+          ptx::mma_mxf8_ss_2cta((d_tmem), adesc + 2 * k, bdesc + 2 * k, ptx::make_idesc_mxf8(2 * BM, HN, 0, 0, k, k), sf_t, \
+                                sf_t + 8, ((kb) | k) != 0 ? 1u : 0u);                                                      \
+      ptx::tc_commit_2cta(&empty[s1], 3);                                                                                  \
+    }                                                                                                                      \
+    if (++s1 == STAGES) s1 = 0;                                                                                            \
+  } while (0)
+      int it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int u0 = 2 * it, u1 = 2 * it + 1;                 // running use index of the accumulator buffers
+        const int b0 = u0 % 3, b1 = u1 % 3;
+        const uint32_t d0 = tmem_u + b0 * HN, d1 = tmem_u + b1 * HN;
+        ptx::mbar_wait(&tempty[b0], ((u0 / 3) & 1) ^ 1);
+        ptx::tc_fence_after();
+        if (lagged) {
+          for (int kb = 0; kb < LAG; ++kb) PA_MX8_H0(kb, d0);
+          ptx::mbar_wait(&tempty[b1], ((u1 / 3) & 1) ^ 1);
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < LAG; ++kb) PA_MX8_H1(kb, d1);
+          for (int kb = LAG; kb < num_k - LAG; ++kb) {
+            PA_MX8_H0(kb, d0);
+            PA_MX8_H1(kb, d1);
+          }
+          for (int kb = num_k - LAG; kb < num_k; ++kb) PA_MX8_H0(kb, d0);
+          if (leader_lane) ptx::tc_commit_2cta(&tfull[b0], 3);
+          for (int kb = num_k - LAG; kb < num_k; ++kb) PA_MX8_H1(kb, d1);
+          if (leader_lane) ptx::tc_commit_2cta(&tfull[b1], 3);
+        } else {
+          ptx::mbar_wait(&tempty[b1], ((u1 / 3) & 1) ^ 1);
+          ptx::tc_fence_after();
+          for (int kb = 0; kb < num_k; ++kb) {
+            PA_MX8_H0(kb, d0);
+            PA_MX8_H1(kb, d1);
+          }
+          if (leader_lane) {
+            ptx::tc_commit_2cta(&tfull[b0], 3);
+            ptx::tc_commit_2cta(&tfull[b1], 3);
+          }
+        }
+      }
+#undef PA_MX8_H0
+#undef PA_MX8_H1
+      __syncwarp();
+    }
+  } else {
+    ptx::setmaxnreg_inc<216>();
+    // eight epilogue warps per CTA: warps 4-7 drain half 0, warps 8-11 half 1 (one warp per TMEM lane quadrant each)
+    const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r_in_tile = q4 * 32 + lane;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      int mt, nt;
+      decode(t, mt, nt);
+      const int b = mt / m_per_batch;
+      const int row = (mt - b * m_per_batch) * 2 * BM + static_cast<int>(rank) * BM + r_in_tile;
+      const int u = 2 * it + half;
+      const int buf = u % 3;
+      ptx::mbar_wait(&tfull[buf], (u / 3) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + buf * HN;
+      const int ng = nt * BN + half * HN;
+      const bool live = ng < p.N;
+      if (p.mode == EPI_QKV_ROPE) {
+        uint32_t areg[128];
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            ptx::tmem_ld_32x32b_x32(taddr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&areg[c * 32]));
+          ptx::tmem_ld_wait();
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(&tempty[buf], 0);
+        if (live) {
+          if (p.bias != nullptr && p.rope != nullptr)
+            epilogue_qkv_from_regs_fast(p, areg, b, row, row < p.rows, ng);
+          else
+            epilogue_qkv_from_regs(p, areg, b, row, row < p.rows, ng);
+        }
+        continue;
+      }
+      if (live) epilogue_tile<HN>(p, taddr, b, row, row < p.rows, ng);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&tempty[buf], 0);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------ quantiser
 // bf16 [batch, rows, K] (strided) -> e4m3 [batch, rows, K] + UE8M0 scales in the chunk layout.
 // One thread per 32-element block.  scale = 2^ceil(log2(amax / 448)); rows >= `rows` of the last 128-row
@@ -601,6 +856,56 @@ static int launch_mx8_pair(const void* A, const void* sfa, const void* W, const 
   return (int)cudaGetLastError();
 }
 
+static int launch_mx8_split(const void* A, const void* sfa, const void* W, const void* sfb, const GemmParams& p,
+                            cudaStream_t st) {
+  using Cfg = Mx8SplitCfg;
+  CUtensorMap ta, tb, tsa, tsb;
+  const int num_k = p.K / 128, m128 = (p.rows + 127) / 128, num_n = (p.N + 255) / 256;
+  {
+    uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
+    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint32_t box[3] = {128, 128, 1};
+    if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.K, (uint64_t)p.N};
+    uint64_t str[2] = {1, (uint64_t)p.K};
+    uint32_t box[2] = {128, 64};
+    if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
+  }
+  {
+    uint64_t dims[2] = {128, (uint64_t)p.batch * m128 * num_k};
+    uint64_t str[2] = {4, 512};
+    uint32_t box[2] = {128, 1};
+    if (make_tmap(&tsa, sfa, 2, dims, str, box, 4, nullptr, false)) return -22;
+    dims[1] = (uint64_t)num_n * 2 * num_k;
+    if (make_tmap(&tsb, sfb, 2, dims, str, box, 4, nullptr, false)) return -23;
+  }
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_mxfp8_2cta_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  const int tiles = ((p.rows + 255) / 256) * p.batch * num_n;
+  const int max_pairs = num_sms() / 2;
+  const int grid = 2 * (tiles < max_pairs ? tiles : max_pairs);
+  gemm_mxfp8_2cta_split_kernel<<<grid, 384, Cfg::SMEM_BYTES, st>>>(ta, tb, tsa, tsb, p);
+  return (int)cudaGetLastError();
+}
+
+static bool mx8_split_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("PA_MXFP8_SPLITN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static bool mx8_pair_default() {
   static int v = -1;
   if (v < 0) {
@@ -619,9 +924,13 @@ int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, G
   if (w_tile != 128 && w_tile != 224 && w_tile != 256) return -11;
   if (p.mode == EPI_QKV_ROPE && w_tile == 224) return -12;
   const bool can_pair = w_tile != 128 && p.rows >= 256;
-  if (pair == 1 && !can_pair) return -13;
-  if (can_pair && (pair == 1 || (pair < 0 && mx8_pair_default()))) {
+  if (pair >= 1 && !can_pair) return -13;
+  if (pair == 2 && w_tile != 256) return -14;
+  if (can_pair && (pair >= 1 || (pair < 0 && mx8_pair_default()))) {
     if (w_tile == 224) return launch_mx8_pair<224, 2>(A, sfa, W, sfb, p, st);
+    // 256-wide tiles: split-N accumulators (three rotating 128-column buffers) unless the classic single accumulator
+    // is asked for (pair == 1 / PA_MXFP8_SPLITN=0)
+    if (pair == 2 || (pair < 0 && mx8_split_default())) return launch_mx8_split(A, sfa, W, sfb, p, st);
     return launch_mx8_pair<256, 1>(A, sfa, W, sfb, p, st);
   }
   CUtensorMap ta, tb;

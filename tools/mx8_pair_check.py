@@ -19,7 +19,7 @@ def rel(a, b):
     return ((a.float() - b.float()).abs().mean() / b.float().abs().mean().clamp_min(1e-9)).item()
 
 
-for (B, M, K, N) in ((1, 256, 256, 256), (1, 256, 1024, 512), (2, 320, 1024, 768), (3, 512, 3072, 1344)):
+for (B, M, K, N) in ((1, 256, 256, 256), (1, 256, 1024, 512), (2, 320, 1024, 768), (3, 512, 3072, 1344), (2, 1024, 3072, 2304)):
     a = torch.randn(B, M, K, device=dev, dtype=torch.bfloat16)
     w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.03
     aq, sfa = ops.quantize_mxfp8(a)
@@ -28,13 +28,14 @@ for (B, M, K, N) in ((1, 256, 256, 256), (1, 256, 1024, 512), (2, 320, 1024, 768
         wq, sfb = ops.quantize_mxfp8(w, tile)
         exact = ad @ ops.dequantize_mxfp8(wq, sfb, tile)[0].t()
         outs = []
-        for pair in (0, 1):
+        for pair in ((0, 1, 2) if tile == 256 else (0, 1)):
             out = torch.zeros(B, M, N, dtype=torch.bfloat16, device=dev)
             ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
             torch.cuda.synchronize()
             outs.append(out)
         res[f"{B}x{M}x{K}x{N}_t{tile}"] = {"pair_vs_exact": rel(outs[1], exact), "one_vs_exact": rel(outs[0], exact),
-                                           "pair_eq_one": bool(torch.equal(outs[0], outs[1]))}
+                                           "pair_eq_one": bool(torch.equal(outs[0], outs[1])),
+                                           "split_eq_one": bool(torch.equal(outs[0], outs[-1]))}
         print(f"{B}x{M}x{K}x{N} t{tile}", res[f"{B}x{M}x{K}x{N}_t{tile}"], flush=True)
 
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -49,7 +50,7 @@ for name, (B, M, K, N, tile) in {"linear1_b8": (8, 4608, 3072, 21504, 256), "lin
     out = torch.empty(B, M, N, dtype=torch.bfloat16, device=dev)
     del a, w
     row = {}
-    for pair in (0, 1):
+    for pair in ((0, 1, 2) if tile == 256 else (0, 1)):
         for _ in range(3):
             ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
         ts = []
@@ -61,7 +62,7 @@ for name, (B, M, K, N, tile) in {"linear1_b8": (8, 4608, 3072, 21504, 256), "lin
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2]
-        row["pair" if pair else "one"] = {"ms": round(ms, 4), "tflops": round(2.0 * B * M * N * K / ms / 1e9, 1)}
+        row[("one", "pair", "pair_split")[pair]] = {"ms": round(ms, 4), "tflops": round(2.0 * B * M * N * K / ms / 1e9, 1)}
     res[name] = row
     print(name, row, flush=True)
 json.dump(res, open("gpurun_out/mx8_pair_check.json", "w"), indent=1)
