@@ -81,6 +81,14 @@ elif which == "mxfp8":
     out = torch.empty(M, N, **bf)
     for _ in range(4):
         ops.gemm_fp8(aq, sfa, wq, sfb, "bias", 224, out=out)
+elif which == "mxfp8_256":     # 256-wide pair tiles, plain epilogue: split-N accumulators (PA_MXFP8_SPLITN=0: single accumulator)
+    M, K, N = 9216, 3072, 9216
+    a, w = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.02
+    aq, sfa = ops.quantize_mxfp8(a)
+    wq, sfb = ops.quantize_mxfp8(w, 256)
+    out = torch.empty(M, N, **bf)
+    for _ in range(4):
+        ops.gemm_fp8(aq, sfa, wq, sfb, "bias", 256, out=out)
 elif which == "mxfp8_l1":      # FLUX single-block linear1 (one sample): drain-first QKV+RoPE epilogue, MXFP8 MLP half
     from comfyui_parallelanything_b200.utils.selfcheck import _rope_table
     H, L, hid, mlp = 24, 4608, 3072, 12288

@@ -13,6 +13,8 @@ SO = os.path.join(ROOT, "comfyui_parallelanything_b200", "ops", "_C.so")
 OUT = os.path.join(ROOT, "profiles", "r2", "sass")
 WANT = {"scatter_patch_embed_kernel": "scatter_patch_embed", "scatter_conv_in_kernel": "scatter_conv_in",
         "gemm_mxfp8_kernelILi256ELi1": "gemm_mxfp8_256x1_drainfirst", "gemm_mxfp8_kernelILi224ELi2": "gemm_mxfp8_224x2",
+        "gemm_mxfp8_2cta_kernelILi224ELi2": "gemm_mxfp8_ctapair_224x2", "gemm_mxfp8_2cta_split_kernel": "gemm_mxfp8_ctapair_splitn",
+        "xattn_cluster_kernel": "xattn_cluster",
         "gemm_bf16_2cta_kernel": "gemm_bf16_2cta", "attention2_kernelILi128ELi0ELi1": "attention2_d128",
         "gn_cluster_kernel": "groupnorm_cluster", "multimem_bcast_kernel": "multimem_bcast", "sp_pull_kernel": "sp_pull",
         "sp_signal_kernel": "sp_signal", "ln_mod_fast_kernelILi12ELi12ELb1": "ln_mod_fp8out",
