@@ -45,6 +45,30 @@ def supported(executors) -> Optional[str]:
     return None
 
 
+def exchange_tables(g: int, n: int, Lt: int, Li: int, hid: int, mlp: int, hpg: int, ptrs):
+    """Copy descriptors (src, dst, src_pitch, dst_pitch, rows, row_bytes) GPU ``g`` pulls with, bf16 buffers:
+    ``ptrs[r]`` = base addresses of rank r's Q / K / V [H, Ll, 128] (all heads, its [txt | img] token slice), QF / KF / VF
+    [hpg, L, 128] (its heads, all tokens in global [txt | img] order), ATTF [L, hpg*128] and CAT [Ll, hid+mlp].
+    Pure function of the geometry (CPU-testable)."""
+    Ltl, Lil = Lt // n, Li // n
+    Ll, L = Ltl + Lil, Lt + Li
+    qkv, att = [], []
+    for r in range(n):
+        for name_l, name_f in (("Q", "QF"), ("K", "KF"), ("V", "VF")):
+            src_base = ptrs[r][name_l] + g * hpg * Ll * 256          # heads of g inside r's [H, Ll, 128]
+            dst_base = ptrs[g][name_f]
+            # txt slice of r -> global rows [r*Ltl, ...), img slice -> global rows [Lt + r*Lil, ...)
+            qkv.append((src_base, dst_base + (r * Ltl) * 256, Ll * 256, L * 256, hpg, Ltl * 256))
+            qkv.append((src_base + Ltl * 256, dst_base + (Lt + r * Lil) * 256, Ll * 256, L * 256, hpg, Lil * 256))
+        # attention output of r's heads for MY token rows -> columns [r*hpg*128, ...) of my CAT rows
+        src = ptrs[r]["ATTF"]
+        dst = ptrs[g]["CAT"] + r * hpg * 256
+        ld = (hid + mlp) * 2
+        att.append((src + (g * Ltl) * hpg * 256, dst, hpg * 256, ld, Ltl, hpg * 256))
+        att.append((src + (Lt + g * Lil) * hpg * 256, dst + Ltl * ld, hpg * 256, ld, Lil, hpg * 256))
+    return qkv, att
+
+
 class FluxUlysses(UlyssesBase):
     """Wires N FluxExecutors (one per GPU, same process) for sequence-parallel batch-1 steps."""
     family = "flux"
@@ -123,21 +147,9 @@ class FluxUlysses(UlyssesBase):
             ws["ROPE"] = torch.stack([pe[0, 0, :, :, 0, 0], pe[0, 0, :, :, 1, 0]], -1).float().contiguous()
             wss.append(ws)
         # descriptor tables (static addresses -> built once, baked into the graphs)
+        ptrs = [{k: ws[k].data_ptr() for k in ("Q", "K", "V", "QF", "KF", "VF", "ATTF", "CAT")} for ws in wss]
         for g, ws in enumerate(wss):
-            qkv, att = [], []
-            for r, wr in enumerate(wss):
-                for name_l, name_f in (("Q", "QF"), ("K", "KF"), ("V", "VF")):
-                    src_base = wr[name_l].data_ptr() + g * hpg * Ll * 256          # heads of g inside r's [H, Ll, 128]
-                    dst_base = ws[name_f].data_ptr()
-                    # txt slice of r -> global rows [r*Ltl, ...), img slice -> global rows [Lt + r*Lil, ...)
-                    qkv.append((src_base, dst_base + (r * Ltl) * 256, Ll * 256, L * 256, hpg, Ltl * 256))
-                    qkv.append((src_base + Ltl * 256, dst_base + (Lt + r * Lil) * 256, Ll * 256, L * 256, hpg, Lil * 256))
-                # attention output of r's heads for MY token rows -> columns [r*hpg*128, ...) of my CAT rows
-                src = wr["ATTF"].data_ptr()
-                dst = ws["CAT"].data_ptr() + r * hpg * 256
-                ld = (hid + mlp) * 2
-                att.append((src + (g * Ltl) * hpg * 256, dst, hpg * 256, ld, Ltl, hpg * 256))
-                att.append((src + (Lt + g * Lil) * hpg * 256, dst + Ltl * ld, hpg * 256, ld, Lil, hpg * 256))
+            qkv, att = exchange_tables(g, n, Lt, Li, hid, mlp, hpg, ptrs)
             ws["DESC_QKV"], ws["N_QKV"] = self._table(qkv, ws["X"].device), len(qkv)
             ws["DESC_ATT"], ws["N_ATT"] = self._table(att, ws["X"].device), len(att)
         self._ws[key] = wss

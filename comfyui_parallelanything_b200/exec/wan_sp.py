@@ -44,6 +44,24 @@ def supported(executors) -> Optional[str]:
     return None
 
 
+def exchange_tables(g: int, n: int, Ll: int, dim: int, hpg: int, ptrs):
+    """Copy descriptors (src, dst, src_pitch, dst_pitch, rows, row_bytes) GPU ``g`` pulls with, bf16 buffers:
+    ``ptrs[r]`` = base addresses of rank r's QKV [Ll, 3*dim] (its tokens, all heads), QF / KF / VF [L, hpg*128] (all
+    tokens, its heads), ATTF [L, hpg*128] and ATT [Ll, dim].  Pure function of the geometry (CPU-testable)."""
+    qkv, att = [], []
+    for r in range(n):
+        for sec, name_f in enumerate(("QF", "KF", "VF")):
+            # heads of g inside r's token-major [Ll, 3*dim] -> rows [r*Ll, ...) of my [L, hpg*128]
+            src = ptrs[r]["QKV"] + (sec * dim + g * hpg * 128) * 2
+            dst = ptrs[g][name_f] + r * Ll * hpg * 256
+            qkv.append((src, dst, 3 * dim * 2, hpg * 256, Ll, hpg * 256))
+        # attention output of r's heads for MY token rows -> columns [r*hpg*128, ...) of my ATT rows
+        src = ptrs[r]["ATTF"] + g * Ll * hpg * 256
+        dst = ptrs[g]["ATT"] + r * hpg * 256
+        att.append((src, dst, hpg * 256, dim * 2, Ll, hpg * 256))
+    return qkv, att
+
+
 class WanUlysses(UlyssesBase):
     family = "wan"
 
@@ -103,18 +121,9 @@ class WanUlysses(UlyssesBase):
             ws["ROPE"] = rope[g * Ll:(g + 1) * Ll].contiguous()       # RoPE rows of MY tokens
             ws["ctx_sig"] = None
             wss.append(ws)
+        ptrs = [{k: ws[k].data_ptr() for k in ("QKV", "QF", "KF", "VF", "ATTF", "ATT")} for ws in wss]
         for g, ws in enumerate(wss):
-            qkv, att = [], []
-            for r, wr in enumerate(wss):
-                for sec, name_f in enumerate(("QF", "KF", "VF")):
-                    # heads of g inside r's token-major [Ll, 3*dim] -> rows [r*Ll, ...) of my [L, hpg*128]
-                    src = wr["QKV"].data_ptr() + (sec * dim + g * hpg * 128) * 2
-                    dst = ws[name_f].data_ptr() + r * Ll * hpg * 256
-                    qkv.append((src, dst, 3 * dim * 2, hpg * 256, Ll, hpg * 256))
-                # attention output of r's heads for MY token rows -> columns [r*hpg*128, ...) of my ATT rows
-                src = wr["ATTF"].data_ptr() + g * Ll * hpg * 256
-                dst = ws["ATT"].data_ptr() + r * hpg * 256
-                att.append((src, dst, hpg * 256, dim * 2, Ll, hpg * 256))
+            qkv, att = exchange_tables(g, n, Ll, dim, hpg, ptrs)
             ws["DESC_QKV"], ws["N_QKV"] = self._table(qkv, ws["X"].device), len(qkv)
             ws["DESC_ATT"], ws["N_ATT"] = self._table(att, ws["X"].device), len(att)
         self._ws[key] = wss
