@@ -40,29 +40,37 @@ for (B, M, K, N) in ((1, 256, 256, 256), (1, 256, 1024, 512), (2, 320, 1024, 768
 
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for name, (B, M, K, N, tile) in {"linear1_b8": (8, 4608, 3072, 21504, 256), "linear2_b8": (8, 4608, 15360, 3072, 224),
-                                 "img_mlp_b8": (8, 4096, 3072, 12288, 224), "txt_mlp_b8": (8, 512, 3072, 12288, 224),
-                                 "linear1_b1": (1, 4608, 3072, 21504, 256), "linear2_b1": (1, 4608, 15360, 3072, 224)}.items():
+SHAPES = {"linear1_b8": (8, 4608, 3072, 21504, (256,)), "linear2_b8": (8, 4608, 15360, 3072, (224, 256)),
+          "img_mlp_b8": (8, 4096, 3072, 12288, (224, 256)), "img_proj_b8": (8, 4096, 3072, 3072, (224, 256)),
+          "txt_mlp_b8": (8, 512, 3072, 12288, (224,)), "linear1_b1": (1, 4608, 3072, 21504, (256,)),
+          "linear2_b1": (1, 4608, 15360, 3072, (224, 256)), "img_proj_b1": (1, 4096, 3072, 3072, (224, 256)),
+          "wan_o_b2": (2, 14400, 5120, 5120, (224, 256)), "wan_ffn2_b2": (2, 14400, 13824, 5120, (224, 256))}
+only = [a for a in sys.argv[1:] if not a.startswith("-")]
+for name, (B, M, K, N, tiles) in SHAPES.items():
+    if only and name not in only:
+        continue
     a = torch.randn(B, M, K, device=dev, dtype=torch.bfloat16)
     w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.02
     aq, sfa = ops.quantize_mxfp8(a)
-    wq, sfb = ops.quantize_mxfp8(w, tile)
     out = torch.empty(B, M, N, dtype=torch.bfloat16, device=dev)
-    del a, w
+    del a
     row = {}
-    for pair in ((0, 1, 2) if tile == 256 else (0, 1)):
-        for _ in range(3):
-            ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
-        ts = []
-        for _ in range(8):
-            flush.fill_(1)
-            e0.record()
-            ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
-        row[("one", "pair", "pair_split")[pair]] = {"ms": round(ms, 4), "tflops": round(2.0 * B * M * N * K / ms / 1e9, 1)}
+    for tile in tiles:
+        wq, sfb = ops.quantize_mxfp8(w, tile)
+        for pair in ((0, 1, 2) if tile == 256 else (0, 1)):
+            for _ in range(3):
+                ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
+            ts = []
+            for _ in range(8):
+                flush.fill_(1)
+                e0.record()
+                ops.gemm_fp8(aq, sfa, wq, sfb, "bias", tile, out=out, pair=pair)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            row[f"t{tile}_" + ("one", "pair", "pair_split")[pair]] = {"ms": round(ms, 4), "tflops": round(2.0 * B * M * N * K / ms / 1e9, 1)}
+    del w
     res[name] = row
     print(name, row, flush=True)
 json.dump(res, open("gpurun_out/mx8_pair_check.json", "w"), indent=1)
