@@ -1,4 +1,4 @@
-"""Shared plumbing of the sequence-parallel (Ulysses) batch-1 paths (``flux_sp.py``, ``wan_sp.py``).
+"""Shared plumbing of the sequence-parallel (Ulysses) batch-1 paths (``flux_sp.py``, ``wan_sp.py``, ``zimage_sp.py``).
 
 One object wires the N native executors of a chain (one per GPU, same process): per-GPU flag arrays, device-resident
 epoch counters and error words, descriptor tables for the peer-pull all-to-all kernel (csrc/comm/sp_a2a.cu), the
@@ -122,6 +122,9 @@ def build(executors, timeout_ms: int = 20000) -> "tuple[Optional[UlyssesBase], O
     elif fam == "wan":
         from . import wan_sp as mod
         cls = mod.WanUlysses
+    elif fam == "zimage":
+        from . import zimage_sp as mod
+        cls = mod.ZImageUlysses
     else:
         return None, "no sequence-parallel path for this model family"
     why = mod.supported(executors)

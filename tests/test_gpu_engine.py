@@ -238,3 +238,36 @@ def test_batch1_sequence_parallel_ulysses_wan(fp8):
     assert eng.metrics.counters.get("ulysses_steps", 0) == 5
     assert all(len(s.replica._graphs) >= 1 for s in eng.slots)
     pa.cleanup_parallel_model(m)
+
+
+@pytest.mark.multigpu
+@pytest.mark.parametrize("fp8", [False, True])
+def test_batch1_sequence_parallel_ulysses_zimage(fp8):
+    """NextDiT at batch 1: image-only exchange tables for the noise refiner, joint [caption | image] tables for the main
+    layers, caption path replicated and cached; result vs the fp32 oracle with a new latent every step."""
+    from comfyui_parallelanything_b200.models import zimage
+    from comfyui_parallelanything_b200.utils.config import EngineConfig
+    n = 2
+    devs = [f"cuda:{i}" for i in range(n)]
+    torch.manual_seed(0)
+    p = zimage.zimage_tiny_params()
+    m = zimage.ZImageModel(p).to(device=devs[0], dtype=torch.bfloat16).eval()
+    oracle = copy.deepcopy(m).float()
+    cfg = EngineConfig(fp8=fp8, batch1_mode="ulysses")
+    pa.ParallelAnything().setup_parallel(m, _chain(devs), config=cfg)
+    eng = m._parallel_engine
+    assert eng._ulysses is not None and eng._ulysses.family == "zimage", "sequence-parallel Z-Image path was not set up"
+    base = zimage.example_inputs(p, 1, 256, 256, cap_len=32, device=devs[0], dtype=torch.bfloat16)
+    rels = []
+    with torch.no_grad():
+        for it in range(5):
+            inp = {k: (v * (1.0 - 0.1 * it)).clone() if k == "x" else v.clone() for k, v in base.items()}
+            got = m(inp["x"], inp["timesteps"], context=inp["context"])
+            want = oracle(**{k: v.float() for k, v in inp.items()})
+            torch.cuda.synchronize()
+            rels.append((got.float() - want).abs().mean().item() / want.abs().mean().item())
+    eng._ulysses.check_error()
+    assert max(rels) < (0.06 if fp8 else 0.03), rels
+    assert eng.metrics.counters.get("ulysses_steps", 0) == 5
+    assert all(len(s.replica._graphs) >= 1 for s in eng.slots)
+    pa.cleanup_parallel_model(m)

@@ -104,3 +104,34 @@ def test_flux_exchange_tables_keep_txt_img_order(n):
         got = cat[:, :hid].reshape(Ll, heads, 128)
         assert np.array_equal(got, full_att[rows_of(g)]), g
         assert not cat[:, hid:].any()                      # the MLP half of the concat buffer is not touched
+
+
+def test_image_only_tables_of_the_nextdit_refiner():
+    """Z-Image's noise refiner attends over the image tokens only: the FLUX table builder with an empty caption segment
+    (zero-sized descriptors dropped, as exec/zimage_sp.py does)."""
+    exchange_tables = _load("flux_sp")
+    n, heads, Li, dim = 2, 4, 32, 4 * 128
+    hpg, Lil = heads // n, Li // n
+    heap = Heap()
+    ptrs = [{"Q": heap.alloc(heads * Lil * 128), "K": heap.alloc(heads * Lil * 128), "V": heap.alloc(heads * Lil * 128),
+             "QF": heap.alloc(hpg * Li * 128), "KF": heap.alloc(hpg * Li * 128), "VF": heap.alloc(hpg * Li * 128),
+             "ATTF": heap.alloc(Li * hpg * 128), "CAT": heap.alloc(Lil * dim)} for _ in range(n)]
+    heap.build()
+    rng = np.random.default_rng(2)
+    full = {k: rng.integers(0, 65535, size=(heads, Li, 128), dtype=np.uint16) for k in "QKV"}
+    full_att = rng.integers(0, 65535, size=(Li, heads, 128), dtype=np.uint16)
+    for r in range(n):
+        for k in "QKV":
+            heap.view(ptrs[r][k], (heads, Lil, 128))[:] = full[k][:, r * Lil:(r + 1) * Lil]
+        heap.view(ptrs[r]["ATTF"], (Li, hpg, 128))[:] = full_att[:, r * hpg:(r + 1) * hpg]
+    for g in range(n):
+        qkv, att = exchange_tables(g, n, 0, Li, dim, 0, hpg, ptrs)
+        qkv = [d for d in qkv if d[4] > 0 and d[5] > 0]
+        att = [d for d in att if d[4] > 0 and d[5] > 0]
+        assert len(qkv) == 3 * n and len(att) == n
+        heap.run(qkv)
+        heap.run(att)
+    for g in range(n):
+        for k in "QKV":
+            assert np.array_equal(heap.view(ptrs[g][k + "F"], (hpg, Li, 128)), full[k][g * hpg:(g + 1) * hpg]), (g, k)
+        assert np.array_equal(heap.view(ptrs[g]["CAT"], (Lil, heads, 128)), full_att[g * Lil:(g + 1) * Lil]), g

@@ -29,104 +29,18 @@ def host_inputs(B, cap_len):
 
 
 def run_nodes(a) -> int:
-    """One process, `Parallel Anything` hooks the model's forward, a sampler-like loop calls it with a NEW latent tensor
-    every step and does the Euler update on the lead GPU.  batch 1 = the video workload: sequence-parallel (Ulysses)."""
-    import time
-    hb.quiet_stdout()
-    rank, world, local = hb.dist_env()
-    if hb.host_only_group(rank, world):
-        return 0
+    """One process through the node API (tools/_nodes_bench.py); batch 1 = the video workload: sequence-parallel."""
     import torch
-    import comfyui_parallelanything_b200 as pa
+    import _nodes_bench
     from comfyui_parallelanything_b200.models import wan
-    lead = torch.device("cuda:0")
-    torch.cuda.set_device(lead)
-    B = a.batch
-    cfg, host = host_inputs(B, a.cap_len)
-    torch.manual_seed(1234)
-    t0 = time.perf_counter()
-    with torch.device(lead):
-        model = wan.WanModel(cfg, dtype=torch.bfloat16).eval()
-    chain = None
-    for i in range(a.gpus):
-        chain = pa.ParallelDevice().add_device(f"cuda:{i}", 100.0 / a.gpus, chain)[0]
-    if a.dtype == "fp8":
-        os.environ["PA_FP8"] = "1"
-    (model,) = pa.ParallelAnything().setup_parallel(model, chain, True, False, True, False)
-    for i in range(a.gpus):
-        torch.cuda.synchronize(i)
-    setup_s = round(time.perf_counter() - t0, 2)
-    eng = model._parallel_engine
-    d = {k: v.to(lead) for k, v in host.items()}
-    stage = {k: torch.empty_like(v, device=lead) for k, v in host.items()}
-    result_host = torch.empty(B, 16, 4, 90, 160, dtype=torch.bfloat16).pin_memory()
+    cfg, host = host_inputs(a.batch, a.cap_len)
 
-    def euler(x, e, sig):
-        return x + (sig[:, 1] - sig[:, 0]).view(-1, 1, 1, 1, 1).to(x.dtype) * e
+    def build(lead):
+        with torch.device(lead):
+            return wan.WanModel(cfg, dtype=torch.bfloat16).eval()
 
-    state = {"x": d["x"]}
-
-    def step_device():
-        with torch.no_grad():
-            x = state["x"]
-            e = model(x, d["timesteps"], context=d["context"])
-            state["x"] = euler(x, e, d["sig"])
-
-    def step_e2e():
-        with torch.no_grad():
-            fresh = {k: torch.empty_like(v) for k, v in stage.items() if k in ("x", "timesteps")}
-            for k in stage:
-                (fresh.get(k, stage[k])).copy_(host[k], non_blocking=True)
-            e = model(fresh["x"], fresh["timesteps"], context=stage["context"])
-            result_host.copy_(euler(fresh["x"], e, stage["sig"]), non_blocking=True)
-
-    def sync_all():
-        for i in range(a.gpus):
-            torch.cuda.synchronize(i)
-
-    def timed_local(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        sync_all()
-        return e0.elapsed_time(e1) / steps
-
-    sampler = hb.ClockSampler()
-    sampler.start()
-    ms = timed_local(step_device, a.steps, max(a.warmup, 4))
-    ms_e2e = timed_local(step_e2e, a.steps, max(3, a.warmup // 2))
-    clocks = sampler.stop(a.gpus)
-    extra = {}
-    if a.gpus > 1:
-        with torch.no_grad():
-            got = model(d["x"], d["timesteps"], context=d["context"]).clone()
-            want = eng.slots[0].replica(d["x"], d["timesteps"], context=d["context"]).clone()
-        sync_all()
-        extra["output_matches_n1"] = hb.rel_err(got, want)
-    if getattr(eng, "_ulysses", None) is not None:
-        eng._ulysses.check_error()
-    desc = eng.describe() if hasattr(eng, "describe") else {}
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = result_host.numel() * result_host.element_size()
-    pa.cleanup_parallel_model(model)
-    hb.host_only_release(world)
-    hb.emit({"metric": hb.METRIC, "value": round(1000.0 / ms, 4), "unit": "steps/s", "n_gpus": a.gpus, "steps": a.steps,
-             "warmup": a.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong",
-             "vs_baseline": None, "sec_per_it": round(ms / 1000.0, 4), "dtype": a.dtype,
-             "data": "synthetic, random-init weights", "impl": "ours", "api": "nodes", "clocks": clocks,
-             "e2e": {"value": round(1000.0 / ms_e2e, 4), "unit": "steps/s", "ms_per_step": round(ms_e2e, 3),
-                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-             "output_finite": bool(torch.isfinite(result_host.float()).all().item()),
-             "setup": {"setup_s": setup_s}, "engine": desc, **extra,
-             "config": {"model": MODEL_NAME, "global_batch": B, "text_len": a.cap_len, "baseline_config": 4,
-                        "parallelism": f"one process, node API, {a.gpus} GPU(s)"
-                                       + (", sequence-parallel (Ulysses)" if B == 1 and a.gpus > 1 else "")}})
-    return 0
+    return _nodes_bench.run(a, hb, MODEL_NAME, build, host,
+                            {"model": MODEL_NAME, "global_batch": a.batch, "text_len": a.cap_len, "baseline_config": 4})
 
 
 def main() -> int:

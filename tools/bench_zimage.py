@@ -31,6 +31,21 @@ def host_inputs(B, cap_len):
     return cfg, {k: v.pin_memory() for k, v in inp.items()}
 
 
+def run_nodes(a) -> int:
+    import torch
+    import _nodes_bench
+    from comfyui_parallelanything_b200.models import zimage
+    cfg, host = host_inputs(a.batch, a.cap_len)
+
+    def build(lead):
+        with torch.device(lead):
+            return zimage.ZImageModel(cfg, dtype=torch.bfloat16).eval()
+
+    return _nodes_bench.run(a, hb, MODEL_NAME, build, host,
+                            {"model": MODEL_NAME, "global_batch": a.batch, "cap_len": a.cap_len,
+                             "published": "26.00 s/it (1x RTX 3090), 12.91 s/it (V100 + RTX 3090), batch 21"})
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -40,7 +55,12 @@ def main() -> int:
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"], help="fp8 = MXFP8 block GEMMs in the native executor")
     ap.add_argument("--batch", type=int, default=21)
     ap.add_argument("--cap-len", type=int, default=256)
+    ap.add_argument("--api", default="spmd", choices=["spmd", "nodes"],
+                    help="nodes = ONE process through the ComfyUI node API, new latent tensor every step (batch 1 -> "
+                         "sequence-parallel over the chain; 30 heads: 2, 3, 5 or 6 GPUs)")
     a = ap.parse_args()
+    if a.api == "nodes":
+        return run_nodes(a)
     hb.quiet_stdout()
     import torch
     rank, world, local = hb.dist_env()
