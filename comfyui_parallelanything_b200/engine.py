@@ -310,7 +310,19 @@ class ParallelEngine:
             n = len(self.slots)
             if batch == 1 and self.config.workload_split and self._ulysses is not None \
                     and self._can_ulysses(x, timesteps, context):
-                return self._forward_ulysses(step, x, timesteps, context, kwargs)
+                try:
+                    return self._forward_ulysses(step, x, timesteps, context, kwargs)
+                except Exception as e:  # noqa: BLE001
+                    if _is_oom(e):
+                        raise
+                    # a stalled / dead peer (flag watchdog), a failed capture, ...: this sample is recomputed on the lead
+                    # replica below and the chain stays on the layer-split / lead path from now on
+                    log.error("sequence-parallel batch-1 step failed (%s); disabling it for this model", e)
+                    self.metrics.incr("ulysses_fallbacks")
+                    try:
+                        self._ulysses.release()
+                    finally:
+                        self._ulysses = None
             if batch == 1 and self.config.workload_split:
                 with pp.pipeline_mode(True):
                     lead = self.slots[0]
@@ -621,6 +633,7 @@ class ParallelEngine:
         (exec/flux_sp.py, exec/wan_sp.py).  Inputs are staged into fixed buffers (a sampler passes fresh tensors), each GPU's share of
         the step is one CUDA graph; the velocity rows land in the lead GPU's output buffer through the fused gather."""
         sp = self._ulysses
+        sp.check_polled()                  # error words of the PREVIOUS step (copied to pinned memory at its end)
         lead_dev = self.lead_device
         lead_stream = torch.cuda.current_stream(lead_dev)
         bf = torch.bfloat16
@@ -707,6 +720,9 @@ class ParallelEngine:
                 for name, e in errors:
                     log.error("on %s: %s", name, e)
                 raise errors[0][1]
+        for g, slot in enumerate(self.slots):
+            with torch.cuda.device(slot.device), torch.cuda.stream(slot.stream):
+                sp.poll_async(g)           # 4-byte D2H per GPU, looked at by the next step (no host sync here)
         self.metrics.incr("ulysses_steps")
         self.metrics.record(step=step, host_ms=(time.perf_counter() - t0) * 1e3, batch=1, sizes=[1], ulysses=True,
                             native_launch=launched)

@@ -36,6 +36,7 @@ class UlyssesBase:
         self.epoch = [torch.ones(1, dtype=torch.int32, device=d) for d in devs]
         self.err = [torch.zeros(1, dtype=torch.int32, device=d) for d in devs]
         self.flag_tab = [torch.tensor([f.data_ptr() for f in self.flags], dtype=torch.int64, device=d) for d in devs]
+        self.err_host = torch.zeros(self.n, dtype=torch.int32).pin_memory()      # polled copies of the error words
         self._ws: Dict[tuple, list] = {}
         self._dry = False
         self.warmed = set()
@@ -102,6 +103,17 @@ class UlyssesBase:
     def _end_step(self, g: int) -> None:
         if not self._dry:
             self.C.sp_epoch_inc(self.epoch[g])
+
+    def poll_async(self, g: int) -> None:
+        """Queue a copy of GPU g's error word to pinned host memory on the current stream (no synchronisation)."""
+        self.err_host[g:g + 1].copy_(self.err[g], non_blocking=True)
+
+    def check_polled(self) -> None:
+        """Raise if a previous step's exchange hit the flag watchdog (values arrive with ``poll_async``)."""
+        for g in range(self.n):
+            v = int(self.err_host[g]) & 0xFFFFFFFF
+            if v:
+                raise RuntimeError(f"sequence-parallel exchange timed out on GPU {g}: 0x{v:08x} (dead or stalled peer)")
 
     def check_error(self) -> None:
         for g, e in enumerate(self.err):

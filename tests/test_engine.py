@@ -315,3 +315,37 @@ def test_xpu_device_scope_matches_reference_branch(monkeypatch):
     with workers.device_scope("cpu"):
         pass
     assert calls == []
+
+
+def test_failed_sequence_parallel_step_falls_back_and_disables_itself():
+    """A batch-1 step whose sequence-parallel path fails (stalled peer caught by the flag watchdog, failed capture, ...)
+    must still return the right sample - recomputed by the layer-split / lead path - and must not be tried again."""
+    m, plain = Toy(), Toy()
+    plain.load_state_dict(m.state_dict())
+    pa.ParallelAnything().setup_parallel(m, chain_of(50, 50))
+    eng = m._parallel_engine
+
+    class Broken:
+        family = "fake"
+        released = False
+
+        def accepts(self, x, context):
+            return True
+
+        def check_polled(self):
+            raise RuntimeError("sequence-parallel exchange timed out on GPU 1: 0xdead1001 (dead or stalled peer)")
+
+        def release(self):
+            Broken.released = True
+
+    eng._ulysses = Broken()
+    x, t, c, y = inputs(1)
+    with torch.no_grad():
+        got = m(x, t, context=c, y=y)
+        assert torch.allclose(got, plain(x, t, context=c, y=y), atol=1e-6)
+        assert eng._ulysses is None and Broken.released
+        assert eng.metrics.counters.get("ulysses_fallbacks", 0) == 1
+        got2 = m(x, t, context=c, y=y)                  # the next batch-1 step goes straight to the layer-split mode
+        assert torch.allclose(got2, got, atol=1e-6)
+    assert eng.metrics.counters.get("ulysses_fallbacks", 0) == 1
+    pa.cleanup_parallel_model(m)
