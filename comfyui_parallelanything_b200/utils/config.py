@@ -52,7 +52,9 @@ class EngineConfig:
     flag_timeout_ms: int = field(default_factory=lambda: int(os.environ.get("PA_FLAG_TIMEOUT_MS", "20000")))
     fp8: bool = field(default_factory=lambda: _env_bool("PA_FP8", False))   # MXFP8 block GEMMs in native executors
     cache_conditioning: bool = True       # do not re-send constant context every step
-    pair_cfg: bool = False                # keep cond/uncond of one sample on one rank
+    # ComfyUI hands the sampler's cond and uncond halves as one 2B batch; PA_PAIR_CFG=1 keeps sample i and i + B
+    # on the same replica (engine._forward_cfg_paired) instead of splitting the 2B rows blindly like the reference
+    pair_cfg: bool = field(default_factory=lambda: _env_bool("PA_PAIR_CFG", False))
     # reference semantics for 1 < batch < n_devices is "lead device only" (ADP:1308); by default we instead give one
     # sample to each of the ``batch`` heaviest devices.  ``PA_SMALL_BATCH=lead`` restores the reference behaviour.
     small_batch: str = field(default_factory=lambda: os.environ.get("PA_SMALL_BATCH", "spread"))
