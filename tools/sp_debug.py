@@ -1,5 +1,7 @@
-import copy, os, sys, torch
-sys.path.insert(0, "/root/repo")
+"""Sequence-parallel debugging aid (2 GPUs): per step and GPU the epoch counter, the watchdog error word and the first flag
+slots, plus the error vs the fp32 oracle.   G=0 disables graphs, STEPS=n runs n steps."""
+import copy, os, sys, torch  # noqa: E401
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import comfyui_parallelanything_b200 as pa
 from comfyui_parallelanything_b200.models import flux
 from comfyui_parallelanything_b200.utils.config import EngineConfig
