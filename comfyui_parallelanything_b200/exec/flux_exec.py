@@ -283,9 +283,20 @@ class FluxExecutor(nn.Module):
             return 1 + self._lin(xms, f"d{i}.{s}.qkv", "qkv_rope", q=Q, k=K, v=V, q_scale=W[f"d{i}.{s}.qs"],
                                  k_scale=W[f"d{i}.{s}.ks"], rope=ROPE, seq_off=seq_off)
 
+        # joint attention of the double blocks straight to MXFP8: the txt / img proj GEMMs read row ranges of ONE
+        # [B, L, hid] e4m3 buffer (scale chunks: L/128 per sample, the img range starts at chunk Lt/128)
+        att8 = fused8 and Lt % 128 == 0 and ws["L"] % 128 == 0 and os.environ.get("PA_FP8_ATT_PROJ", "1") != "0"
+        if att8:
+            sf_img = ws["XM8_SF"][(Lt // 128) * (hid // 128) * 512:]
+            A8 = {"img": (ws["XM8"][:, Lt:], sf_img), "txt": (ws["XM8"][:, :Lt], ws["XM8_SF"])}
+
         def post(i, s, xs, xms, a, mh):
             k = ("d", i, s)
-            m = self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
+            if att8 and f"d{i}.{s}.proj.q" in W:
+                m = self._lin(None, f"d{i}.{s}.proj", "gate_res", a8=A8[s], sfa_mtiles=ws["L"] // 128, out=xs, residual=xs,
+                              gate=self._mod(ws, k, 2))
+            else:
+                m = self._lin(a, f"d{i}.{s}.proj", "gate_res", out=xs, residual=xs, gate=self._mod(ws, k, 2))
             if fused8 and f"d{i}.{s}.mlp0.q" in W and f"d{i}.{s}.mlp2.q" in W:
                 a8 = ln8(xs, s, self._mod(ws, k, 4), self._mod(ws, k, 3))
                 m8 = (ws["MH8I"], ws["MH8I_SF"]) if s == "img" else (ws["MH8T"], ws["MH8T_SF"])
@@ -318,7 +329,10 @@ class FluxExecutor(nn.Module):
         for i in range(self.n_double):
           with nvtx_range(f"flux.double[{i}]"):
             n += both(lambda: pre(i, "img", Xi, XMi, Lt), lambda: pre(i, "txt", Xt, XMt, 0))
-            ops.attention(Q, K, V, out=ATT)
+            if att8 and f"d{i}.img.proj.q" in W and f"d{i}.txt.proj.q" in W:
+                C.attention_fp8out(Q, K, V, ws["XM8"], ws["XM8_SF"], 128 ** -0.5)
+            else:
+                ops.attention(Q, K, V, out=ATT)
             n += 1
             n += both(lambda: post(i, "img", Xi, XMi, ATT[:, Lt:], MH[:, Lt:]),
                       lambda: post(i, "txt", Xt, XMt, ATT[:, :Lt], MH[:, :Lt]))

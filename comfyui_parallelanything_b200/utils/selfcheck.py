@@ -758,6 +758,28 @@ def gemm_mxfp8():
 
 
 @check
+def gemm_mxfp8_row_range_operand():
+    """A operand = a row range of a larger [B, L, K] MXFP8 buffer (how the txt / img proj GEMMs of a FLUX double block read
+    the joint attention output): strided batch + `sfa_mtiles`, must equal the GEMM over a contiguous copy bit for bit."""
+    B, L, K, N, r0 = 2, 640, 1024, 768, 128
+    a, w, bias = _rand(B, L, K), _rand(N, K, scale=0.03), _rand(N)
+    aq, sfa = ops.quantize_mxfp8(a)
+    sub_q, sub_sf = ops.quantize_mxfp8(a[:, r0:].contiguous())
+    ok, worst = True, 0.0
+    for tile, pair in ((224, 0), (224, 1), (256, 1), (256, 2)):
+        wq, sfb = ops.quantize_mxfp8(w, tile)
+        want = torch.zeros(B, L - r0, N, dtype=torch.bfloat16, device=_dev())
+        got = torch.zeros_like(want)
+        ops.gemm_fp8(sub_q, sub_sf, wq, sfb, "bias", tile, out=want, bias=bias, pair=pair)
+        ops.gemm_fp8(aq[:, r0:], sfa[(r0 // 128) * (K // 128) * 512:], wq, sfb, "bias", tile, out=got, bias=bias, pair=pair,
+                     sfa_mtiles=L // 128)
+        torch.cuda.synchronize()
+        ok = ok and bool(torch.equal(got, want))
+        worst = max(worst, (got.float() - want.float()).abs().max().item())
+    return {"name": "gemm_mxfp8_row_range_operand", "ok": ok, "max_abs": worst}
+
+
+@check
 def gemm_mxfp8_flux_shape():
     M, K, N = 4608, 3072, 9216
     a, w = _rand(M, K), _rand(N, K, scale=0.02)

@@ -106,8 +106,8 @@ static void gemm(Tensor A, Tensor W, int mode, py::kwargs kw) {
 
 // MXFP8: A_q / W_q are uint8 (e4m3 bit patterns) contiguous, sfa / sfb uint8 scale chunks (see gemm_mxfp8.cu)
 static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, int w_tile, py::kwargs kw) {
-  TORCH_CHECK(A.is_cuda() && A.is_contiguous() && W.is_contiguous() && A.element_size() == 1 && W.element_size() == 1,
-              "gemm_fp8: contiguous 1-byte operands required");
+  TORCH_CHECK(A.is_cuda() && W.is_contiguous() && A.element_size() == 1 && W.element_size() == 1 && A.stride(-1) == 1,
+              "gemm_fp8: 1-byte operands, contiguous rows required");
   c10::cuda::CUDAGuard guard(A.device());
   pa::GemmParams p{};
   long long lda, abs_;
@@ -115,11 +115,18 @@ static void gemm_fp8(Tensor A, Tensor sfa, Tensor W, Tensor sfb, int mode, int w
   p.N = (int)W.size(0);
   p.K = (int)W.size(1);
   TORCH_CHECK(A.size(-1) == p.K, "gemm_fp8: K mismatch");
+  // A may be a row range of a larger [B, L, K] buffer (rows contiguous, batch stride L*K): pass `sfa_mtiles` = L/128 and a
+  // scale tensor that starts at the range's first 128-row chunk
+  TORCH_CHECK(lda == p.K, "gemm_fp8: rows of A must be contiguous (lda == K)");
+  p.sfa_mtiles = has(kw, "sfa_mtiles") ? kw["sfa_mtiles"].cast<int>() : 0;
+  TORCH_CHECK(p.batch == 1 || abs_ == (long long)p.rows * p.K || p.sfa_mtiles > 0,
+              "gemm_fp8: a strided batch needs sfa_mtiles");
   p.mode = mode;
   parse_epilogue(kw, p, /*check_shape=*/true);
   parse_modes(mode, kw, p);
   const int pair = has(kw, "pair") ? kw["pair"].cast<int>() : -1;      // -1 auto | 0 one-CTA kernel | 1 CTA pairs
-  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, w_tile, cur_stream(), pair),
+  check(pa::gemm_mxfp8(A.data_ptr(), sfa.data_ptr(), W.data_ptr(), sfb.data_ptr(), p, w_tile, cur_stream(), pair,
+                       p.batch > 1 ? abs_ : 0),
         "gemm_mxfp8");
 }
 

@@ -33,7 +33,7 @@ int gemm_bf16(const void* A, long long lda, long long a_bstride, const void* W, 
 int quantize_mxfp8_rows(const void* x, long long ldx, long long x_bs, void* q, void* sf, int batch, int rows, int K,
                         int tile_rows, cudaStream_t st);
 int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
-               cudaStream_t st, int pair = -1);   // pair: -1 auto, 0 one CTA per tile, 1 CTA pairs (single accumulator for 256-wide tiles), 2 CTA pairs + split-N accumulators
+               cudaStream_t st, int pair = -1, long long a_bstride = 0);   // a_bstride: bytes between batch entries of A (0: rows*K)   // pair: -1 auto, 0 one CTA per tile, 1 CTA pairs (single accumulator for 256-wide tiles), 2 CTA pairs + split-N accumulators
 
 // out = LN(x) * (1 + scale[b]) + shift[b]   (scale/shift optional; gamma/beta optional affine)
 int rmsnorm_mod(const void* x, long long ldx, long long x_bs, void* out, long long ldo, long long o_bs,

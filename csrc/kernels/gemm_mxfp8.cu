@@ -100,6 +100,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_n = (p.N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = p.K / BK;                      // K % 128 == 0 (checked on the host)
+  const int sfa_mt = p.sfa_mtiles > 0 ? p.sfa_mtiles : m_per_batch;      // scale chunks per batch entry of A's buffer
   constexpr int GROUP_M = 8;
   auto decode = [&](int t, int& mt, int& nt) {
     const int per_group = GROUP_M * num_n;
@@ -127,7 +128,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int mt, nt;
       decode(t, mt, nt);
       const int b = mt / m_per_batch, mrow = (mt - b * m_per_batch) * BM;
-      const uint8_t* sfa_t = sfa + static_cast<long long>(mt) * num_k * 512;
+      const uint8_t* sfa_t = sfa + (static_cast<long long>(b) * sfa_mt + (mt - b * m_per_batch)) * num_k * 512;
       const uint8_t* sfb_t = sfb + static_cast<long long>(nt) * NCHUNK * num_k * 512;
       for (int kb = 0; kb < num_k; ++kb) {
         ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -353,7 +354,7 @@ gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // a pair whose second half lies beyond `rows` still loads (zero-filled) A rows; its scale chunk is clamped
         // to the last real one (those accumulator rows are never stored)
         const int m128 = min(mp * 2 + static_cast<int>(rank), m128_per_batch - 1);
-        const int sfa_row = (b * m128_per_batch + m128) * num_k;
+        const int sfa_row = (b * (p.sfa_mtiles > 0 ? p.sfa_mtiles : m128_per_batch) + m128) * num_k;
         const int sfb_row = nt * NCHUNK * num_k;
         for (int kb = 0; kb < num_k; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -571,7 +572,7 @@ gemm_mxfp8_2cta_split_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         const int mrow = mp * 2 * BM + static_cast<int>(rank) * BM;
         const int nrow = nt * BN + static_cast<int>(rank) * (HN / 2);       // + h * 128 for half h
         const int m128 = min(mp * 2 + static_cast<int>(rank), m128_per_batch - 1);
-        const int sfa_row = (b * m128_per_batch + m128) * num_k;
+        const int sfa_row = (b * (p.sfa_mtiles > 0 ? p.sfa_mtiles : m128_per_batch) + m128) * num_k;
         const int sfb_row = nt * 2 * num_k;
         for (int kb = 0; kb < num_k; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -816,13 +817,13 @@ static int launch_mx8(const CUtensorMap& ta, const CUtensorMap& tb, const void* 
 
 template <int BN, int ACC>
 static int launch_mx8_pair(const void* A, const void* sfa, const void* W, const void* sfb, const GemmParams& p,
-                           cudaStream_t st) {
+                           long long a_bstride, cudaStream_t st) {
   using Cfg = Mx8PairCfg<BN, ACC>;
   CUtensorMap ta, tb, tsa, tsb;
   const int num_k = p.K / 128, m128 = (p.rows + 127) / 128, num_n = (p.N + BN - 1) / BN;
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
-    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint64_t str[3] = {1, (uint64_t)p.K, a_bstride > 0 ? (uint64_t)a_bstride : (uint64_t)p.rows * p.K};
     uint32_t box[3] = {128, 128, 1};
     if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
   }
@@ -833,7 +834,7 @@ static int launch_mx8_pair(const void* A, const void* sfa, const void* W, const 
     if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
   }
   {   // scale chunks as rows of 128 x u32
-    uint64_t dims[2] = {128, (uint64_t)p.batch * m128 * num_k};
+    uint64_t dims[2] = {128, (uint64_t)p.batch * (p.sfa_mtiles > 0 ? p.sfa_mtiles : m128) * num_k};
     uint64_t str[2] = {4, 512};
     uint32_t box[2] = {128, 1};
     if (make_tmap(&tsa, sfa, 2, dims, str, box, 4, nullptr, false)) return -22;
@@ -857,13 +858,13 @@ static int launch_mx8_pair(const void* A, const void* sfa, const void* W, const 
 }
 
 static int launch_mx8_split(const void* A, const void* sfa, const void* W, const void* sfb, const GemmParams& p,
-                            cudaStream_t st) {
+                            long long a_bstride, cudaStream_t st) {
   using Cfg = Mx8SplitCfg;
   CUtensorMap ta, tb, tsa, tsb;
   const int num_k = p.K / 128, m128 = (p.rows + 127) / 128, num_n = (p.N + 255) / 256;
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
-    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint64_t str[3] = {1, (uint64_t)p.K, a_bstride > 0 ? (uint64_t)a_bstride : (uint64_t)p.rows * p.K};
     uint32_t box[3] = {128, 128, 1};
     if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
   }
@@ -874,7 +875,7 @@ static int launch_mx8_split(const void* A, const void* sfa, const void* W, const
     if (make_tmap(&tb, W, 2, dims, str, box, 1, nullptr)) return -21;
   }
   {
-    uint64_t dims[2] = {128, (uint64_t)p.batch * m128 * num_k};
+    uint64_t dims[2] = {128, (uint64_t)p.batch * (p.sfa_mtiles > 0 ? p.sfa_mtiles : m128) * num_k};
     uint64_t str[2] = {4, 512};
     uint32_t box[2] = {128, 1};
     if (make_tmap(&tsa, sfa, 2, dims, str, box, 4, nullptr, false)) return -22;
@@ -919,7 +920,7 @@ static bool mx8_pair_default() {
 // `w_tile` = 224 (generic epilogues, double-buffered accumulators), 256 (fused QKV epilogue) or 128.
 // 224- and 256-wide tiles run on CTA pairs (256 x w_tile per pair) when every batch entry has at least 256 rows.
 int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, GemmParams p, int w_tile,
-               cudaStream_t st, int pair) {
+               cudaStream_t st, int pair, long long a_bstride) {
   if (p.K % 128 || p.N % 32) return -10;
   if (w_tile != 128 && w_tile != 224 && w_tile != 256) return -11;
   if (p.mode == EPI_QKV_ROPE && w_tile == 224) return -12;
@@ -927,16 +928,16 @@ int gemm_mxfp8(const void* A, const void* sfa, const void* W, const void* sfb, G
   if (pair >= 1 && !can_pair) return -13;
   if (pair == 2 && w_tile != 256) return -14;
   if (can_pair && (pair >= 1 || (pair < 0 && mx8_pair_default()))) {
-    if (w_tile == 224) return launch_mx8_pair<224, 2>(A, sfa, W, sfb, p, st);
+    if (w_tile == 224) return launch_mx8_pair<224, 2>(A, sfa, W, sfb, p, a_bstride, st);
     // 256-wide tiles: split-N accumulators (three rotating 128-column buffers) unless the classic single accumulator
     // is asked for (pair == 1 / PA_MXFP8_SPLITN=0)
-    if (pair == 2 || (pair < 0 && mx8_split_default())) return launch_mx8_split(A, sfa, W, sfb, p, st);
-    return launch_mx8_pair<256, 1>(A, sfa, W, sfb, p, st);
+    if (pair == 2 || (pair < 0 && mx8_split_default())) return launch_mx8_split(A, sfa, W, sfb, p, a_bstride, st);
+    return launch_mx8_pair<256, 1>(A, sfa, W, sfb, p, a_bstride, st);
   }
   CUtensorMap ta, tb;
   {
     uint64_t dims[3] = {(uint64_t)p.K, (uint64_t)p.rows, (uint64_t)p.batch};
-    uint64_t str[3] = {1, (uint64_t)p.K, (uint64_t)p.rows * p.K};
+    uint64_t str[3] = {1, (uint64_t)p.K, a_bstride > 0 ? (uint64_t)a_bstride : (uint64_t)p.rows * p.K};
     uint32_t box[3] = {128, 128, 1};
     if (make_tmap(&ta, A, 3, dims, str, box, 1, nullptr)) return -20;
   }

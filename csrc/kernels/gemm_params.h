@@ -56,6 +56,8 @@ struct GemmParams {
   long long xout_sample_off;        // first sample of this rank inside x_out
   const float* sigmas;              // [batch, 2] (sigma, sigma_next) per sample, or nullptr => out = v
   int C, Hl, Wl, ps;
+  int sfa_mtiles;                   // block-scaled fp8: 128-row scale chunks per batch entry of the A operand's buffer (0: ceil(rows/128));
+                                    // lets a row range of a larger [B, L, K] buffer (txt / img rows of the joint attention output) be an operand
   int tok_off;                      // EULER_UNPATCH: global token index of row 0 (sequence-parallel replicas own a token range)
   // implicit-GEMM convolution: A is an NHWC activation addressed through a 4-D TMA tensor
   // (C, W, H, N); the K loop walks taps x Cin-blocks with shifted spatial coordinates, padding
