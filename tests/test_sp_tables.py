@@ -135,3 +135,28 @@ def test_image_only_tables_of_the_nextdit_refiner():
         for k in "QKV":
             assert np.array_equal(heap.view(ptrs[g][k + "F"], (hpg, Li, 128)), full[k][g * hpg:(g + 1) * hpg]), (g, k)
         assert np.array_equal(heap.view(ptrs[g]["CAT"], (Lil, heads, 128)), full_att[g * Lil:(g + 1) * Lil]), g
+
+
+def test_staging_copies_conditioning_only_when_it_changed():
+    """UlyssesBase.stage: the timestep is copied every step, the conditioning only when the source tensor object / storage /
+    version changed (the reference re-sends constant conditioning every step)."""
+    import torch
+    spec = importlib.util.spec_from_file_location("_sp_common_src", os.path.join(
+        ROOT, "comfyui_parallelanything_b200", "exec", "sp_common.py"))
+    src = open(spec.origin).read().replace("from .. import ops", "ops = None")
+    ns = {"__name__": "_sp_common_src"}
+    exec(compile(src, spec.origin, "exec"), ns)
+    base = object.__new__(ns["UlyssesBase"])                 # no GPUs: skip __init__, stage() needs no state
+    ctx = torch.randn(1, 8, 16)
+    st = {"t": torch.zeros(1, dtype=torch.bfloat16), "ctx": torch.zeros(1, 8, 16, dtype=torch.bfloat16), "ctx_src": None}
+    base.stage(st, torch.tensor([0.75]), ctx, {}, True)
+    assert float(st["t"]) == 0.75 and torch.allclose(st["ctx"].float(), ctx, atol=0.02)
+    v0 = st["ctx"]._version
+    base.stage(st, torch.tensor([0.5]), ctx, {}, True)
+    assert float(st["t"]) == 0.5 and st["ctx"]._version == v0, "unchanged conditioning was copied again"
+    ctx.mul_(2.0)                                            # in-place edit bumps the version -> copied again
+    base.stage(st, torch.tensor([0.5]), ctx, {}, True)
+    assert st["ctx"]._version > v0 and torch.allclose(st["ctx"].float(), ctx, atol=0.04)
+    v1 = st["ctx"]._version
+    base.stage(st, torch.tensor([0.5]), ctx, {}, False)      # caching off: always copied
+    assert st["ctx"]._version > v1
