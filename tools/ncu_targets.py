@@ -81,6 +81,19 @@ elif which == "mxfp8":
     out = torch.empty(M, N, **bf)
     for _ in range(4):
         ops.gemm_fp8(aq, sfa, wq, sfb, "bias", 224, out=out)
+elif which == "xattn":         # SDXL cross-attention (77 keys, head_dim 64, 1024 queries x 20 heads x 16 samples): CTA-pair kernel
+    q = torch.randn(16, 20, 1024, 64, **bf)
+    k, v = torch.randn(16, 20, 77, 64, **bf), torch.randn(16, 20, 77, 64, **bf)
+    out = torch.empty(16, 1024, 20 * 64, **bf)
+    for _ in range(4):
+        ops.attention(q, k, v, out=out, variant=5)
+elif which == "groupnorm":     # SDXL first-level GroupNorm + SiLU: 16 x 16384 x 320 (cluster of 8 CTAs per sample / channel slab)
+    x = torch.randn(16, 128 * 128, 320, **bf)
+    g, b_ = torch.randn(320, **bf), torch.randn(320, **bf)
+    o = torch.empty_like(x)
+    C_ = ops.require()
+    for _ in range(4):
+        C_.groupnorm_silu(x, o, g, b_, 32, 1e-5, True)
 elif which == "mxfp8_256":     # 256-wide pair tiles, plain epilogue: split-N accumulators (PA_MXFP8_SPLITN=0: single accumulator)
     M, K, N = 9216, 3072, 9216
     a, w = torch.randn(M, K, **bf), torch.randn(N, K, **bf) * 0.02
